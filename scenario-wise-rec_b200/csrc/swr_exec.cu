@@ -1,0 +1,267 @@
+// swr_exec.cu -- the C ABI (include/swr_b200.h): direct K1/K2 entry points and the
+// program executor that decodes op records into kernel launches.  No allocation, no
+// synchronisation: everything is enqueued on the caller's stream (graph-capturable).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "swr_common.cuh"
+#include "swr_launch.h"
+
+namespace swr {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- record decoding ------------------------------------------------------------------
+struct Ctx {
+  void* const* slots;
+  int n_slots;
+  bool ok;
+  void* slot(int idx) {
+    if (idx < 0) return nullptr;
+    if (idx >= n_slots) { ok = false; set_error("program: slot %d out of range (%d slots)", idx, n_slots); return nullptr; }
+    return slots[idx];
+  }
+};
+
+// ActRef layout inside a record (see DESIGN.md "Program records"):
+//   s[sb+0] raw  s[sb+1] stats  s[sb+2] rmean  s[sb+3] rvar  s[sb+4] gamma  s[sb+5] gamma2
+//   s[sb+6] beta s[sb+7] beta2  s[sb+8] dz     s[sb+9] dstats (s[sb+10], s[sb+11] reserved)
+//   i[ib+0] ld   i[ib+1] n      i[ib+2] norm mode           i[ib+3] activation
+//   f[fb+0] eps  f[fb+1] var_scale
+static ActDev decode_act(const swr_rec_t& r, int sb, int ib, int fb, Ctx& c) {
+  ActDev a{};
+  a.raw = static_cast<const float*>(c.slot(r.s[sb + 0]));
+  a.norm.stats = static_cast<const double*>(c.slot(r.s[sb + 1]));
+  a.norm.rmean = static_cast<const float*>(c.slot(r.s[sb + 2]));
+  a.norm.rvar = static_cast<const float*>(c.slot(r.s[sb + 3]));
+  a.norm.gamma = static_cast<const float*>(c.slot(r.s[sb + 4]));
+  a.norm.gamma2 = static_cast<const float*>(c.slot(r.s[sb + 5]));
+  a.norm.beta = static_cast<const float*>(c.slot(r.s[sb + 6]));
+  a.norm.beta2 = static_cast<const float*>(c.slot(r.s[sb + 7]));
+  a.dz = static_cast<float*>(c.slot(r.s[sb + 8]));
+  a.dstats = static_cast<double*>(c.slot(r.s[sb + 9]));
+  a.ld = r.i[ib + 0]; a.n = r.i[ib + 1]; a.norm.mode = r.i[ib + 2]; a.act = r.i[ib + 3];
+  a.norm.eps = r.f[fb + 0]; a.norm.var_scale = r.f[fb + 1];
+  if (a.norm.mode == SWR_NORM_BATCH && !a.norm.stats) { c.ok = false; set_error("program: batch-norm activation without statistics"); }
+  if (a.norm.mode == SWR_NORM_RUNNING && (!a.norm.rmean || !a.norm.rvar)) { c.ok = false; set_error("program: running-norm activation without buffers"); }
+  return a;
+}
+
+static FcGroup decode_fc(const swr_rec_t& r, Ctx& c) {
+  FcGroup g{};
+  g.A = decode_act(r, 0, 0, 0, c);
+  g.Y = decode_act(r, 12, 4, 2, c);
+  g.W = static_cast<const float*>(c.slot(r.s[24])); g.W2 = static_cast<const float*>(c.slot(r.s[25]));
+  g.bias = static_cast<const float*>(c.slot(r.s[26])); g.bias2 = static_cast<const float*>(c.slot(r.s[27]));
+  g.dW = static_cast<float*>(c.slot(r.s[28])); g.dW2 = static_cast<float*>(c.slot(r.s[29]));
+  g.dbias = static_cast<float*>(c.slot(r.s[30])); g.dbias2 = static_cast<float*>(c.slot(r.s[31]));
+  g.w_layout = r.i[8]; g.ldw = r.i[9]; g.e_act = r.i[10]; g.flags = r.i[11]; g.e_scale = r.f[4];
+  g.stats_out = (g.Y.norm.mode == SWR_NORM_BATCH) ? const_cast<double*>(g.Y.norm.stats) : nullptr;
+  return g;
+}
+
+static int run_fc(int kind, const swr_rec_t* subs, int n, int64_t B, Ctx& c, cudaStream_t st) {
+  std::vector<FcGroup> groups(n);
+  for (int i = 0; i < n; ++i) groups[i] = decode_fc(subs[i], c);
+  if (!c.ok) return SWR_ERR_INVALID;
+  for (int o = 0; o < n; o += kMaxGroups) {
+    const int m = n - o < kMaxGroups ? n - o : kMaxGroups;
+    int rc;
+    if (kind == SWR_OP_FC_FWD) rc = launch_fc_fwd(groups.data() + o, m, B, st);
+    else if (kind == SWR_OP_FC_WGRAD) rc = launch_fc_wgrad(groups.data() + o, m, B, st);
+    else {
+      // fan-in chunks after the first accumulate into the destination
+      if (o > 0) for (int i = 0; i < m; ++i) groups[o + i].flags |= FC_A_ACCUMULATE;
+      rc = launch_fc_dgrad(groups.data() + o, m, B, st);
+    }
+    if (rc) return rc;
+  }
+  return SWR_OK;
+}
+
+static int run_gather(const swr_rec_t& h, const swr_rec_t* subs, Ctx& c, cudaStream_t st) {
+  const int n = h.n_sub;
+  std::vector<const float*> tables; std::vector<int64_t> vocab; std::vector<const void*> idx; std::vector<int32_t> idt, E;
+  std::vector<const void*> dense; std::vector<int32_t> ddt;
+  for (int i = 0; i < n; ++i) {
+    const swr_rec_t& r = subs[i];
+    if (r.i[4] == 0) {
+      tables.push_back(static_cast<const float*>(c.slot(r.s[0]))); idx.push_back(c.slot(r.s[1]));
+      vocab.push_back(((int64_t)(uint32_t)r.i[0]) | ((int64_t)r.i[1] << 32)); idt.push_back(r.i[2]); E.push_back(r.i[5]);
+    } else {
+      dense.push_back(c.slot(r.s[0])); ddt.push_back(r.i[2]);
+    }
+  }
+  if (!c.ok) return SWR_ERR_INVALID;
+  GatherLaunch g{tables.data(), vocab.data(), idx.data(), idt.data(), E.data(), dense.data(), ddt.data(),
+                 static_cast<float*>(c.slot(h.s[0])), h.i[4], h.i[0], (int)tables.size(), (int)dense.size(),
+                 static_cast<int32_t*>(c.slot(h.s[1]))};
+  return launch_gather(g, st);
+}
+
+static int run_scatter(const swr_rec_t& h, const swr_rec_t* subs, Ctx& c, cudaStream_t st) {
+  const int n = h.n_sub;
+  std::vector<float*> gt(n); std::vector<int64_t> vocab(n); std::vector<const void*> idx(n); std::vector<int32_t> idt(n), E(n), col(n);
+  for (int i = 0; i < n; ++i) {
+    const swr_rec_t& r = subs[i];
+    gt[i] = static_cast<float*>(c.slot(r.s[0])); idx[i] = c.slot(r.s[1]);
+    vocab[i] = ((int64_t)(uint32_t)r.i[0]) | ((int64_t)r.i[1] << 32); idt[i] = r.i[2]; col[i] = r.i[3]; E[i] = r.i[5];
+  }
+  if (!c.ok) return SWR_ERR_INVALID;
+  ScatterLaunch s{static_cast<const float*>(c.slot(h.s[0])), h.i[4], h.i[0], idx.data(), idt.data(), gt.data(), vocab.data(),
+                  E.data(), col.data(), n};
+  return launch_scatter(s, st);
+}
+
+static int run_pool(const swr_rec_t& h, const swr_rec_t* subs, bool bwd, Ctx& c, cudaStream_t st) {
+  const int ng = h.i[2], ne = h.i[3];
+  if (ng + ne != h.n_sub) { set_error("pool: record count mismatch"); return SWR_ERR_INVALID; }
+  std::vector<PoolGate> gates(ng); std::vector<ActDev> experts(ne);
+  for (int g = 0; g < ng; ++g) {
+    const swr_rec_t& r = subs[g];
+    PoolGate& G = gates[g];
+    G.gate = decode_act(r, 0, 0, 0, c);
+    const ActDev out = decode_act(r, 12, 4, 2, c);
+    G.pooled = const_cast<float*>(out.raw); G.dpooled = out.dz; G.ldp = out.ld;
+    G.probs = static_cast<float*>(c.slot(r.s[24]));
+    G.nE = r.i[8];
+    if (G.nE < 0 || G.nE > kMaxPoolExperts) { set_error("pool: gate over %d experts unsupported", G.nE); return SWR_ERR_UNSUPPORTED; }
+    for (int e = 0; e < kMaxPoolExperts; ++e) G.expert[e] = r.i[16 + e];
+  }
+  for (int u = 0; u < ne; ++u) experts[u] = decode_act(subs[ng + u], 0, 0, 0, c);
+  if (!c.ok) return SWR_ERR_INVALID;
+  PoolLaunch l{gates.data(), ng, experts.data(), ne, h.i[0], h.i[1]};
+  return bwd ? launch_pool_bwd(l, st) : launch_pool_fwd(l, st);
+}
+
+static int run_head(const swr_rec_t& h, const swr_rec_t* subs, bool bwd, Ctx& c, cudaStream_t st) {
+  const int nd = h.n_sub;
+  std::vector<HeadDomain> dom(nd);
+  for (int d = 0; d < nd; ++d) {
+    const swr_rec_t& r = subs[d];
+    dom[d].A = decode_act(r, 0, 0, 0, c);
+    dom[d].w = static_cast<const float*>(c.slot(r.s[24])); dom[d].bias = static_cast<const float*>(c.slot(r.s[26]));
+    dom[d].dw = static_cast<float*>(c.slot(r.s[28])); dom[d].dbias = static_cast<float*>(c.slot(r.s[30]));
+  }
+  HeadLaunch l{dom.data(), nd, c.slot(h.s[0]), h.i[3], static_cast<float*>(c.slot(h.s[1])),
+               static_cast<const float*>(c.slot(h.s[2])), static_cast<const float*>(c.slot(h.s[3])),
+               static_cast<float*>(c.slot(h.s[4])), h.i[2], h.i[0]};
+  if (!c.ok) return SWR_ERR_INVALID;
+  return bwd ? launch_head_bwd(l, st) : launch_head_fwd(l, st);
+}
+
+static int run_bn(const swr_rec_t& h, const swr_rec_t* subs, bool pgrad, Ctx& c, cudaStream_t st) {
+  const int n = h.n_sub;
+  std::vector<BnLayer> layers(n);
+  for (int i = 0; i < n; ++i) {
+    const swr_rec_t& r = subs[i];
+    layers[i].A = decode_act(r, 0, 0, 0, c);
+    if (pgrad) {
+      layers[i].dgamma = static_cast<float*>(c.slot(r.s[24])); layers[i].dgamma2 = static_cast<float*>(c.slot(r.s[25]));
+      layers[i].dbeta = static_cast<float*>(c.slot(r.s[26])); layers[i].dbeta2 = static_cast<float*>(c.slot(r.s[27]));
+    } else {
+      layers[i].rmean = const_cast<float*>(layers[i].A.norm.rmean); layers[i].rvar = const_cast<float*>(layers[i].A.norm.rvar);
+      layers[i].nbt = static_cast<int64_t*>(c.slot(r.s[24]));
+    }
+  }
+  if (!c.ok) return SWR_ERR_INVALID;
+  return pgrad ? launch_bn_pgrad(layers.data(), n, h.i[0], st) : launch_bn_update(layers.data(), n, h.i[0], h.f[4], st);
+}
+
+}  // namespace swr
+
+using namespace swr;
+
+extern "C" {
+
+SWR_API int swr_abi_version(void) { return SWR_ABI_VERSION; }
+SWR_API const char* swr_last_error(void) { return g_err; }
+SWR_API int64_t swr_launch_count(void) { return g_launches.load(); }
+
+SWR_API int swr_device_check(void) {
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    set_error("no CUDA device"); return SWR_ERR_NO_DEVICE;
+  }
+  if (prop.major != 10) { set_error("device sm_%d%d is not sm_100-class", prop.major, prop.minor); return SWR_ERR_NO_DEVICE; }
+  return SWR_OK;
+}
+
+SWR_API int swr_embedding_gather_fwd(const float* const* tables, const int64_t* vocab, const void* const* idx,
+                             const int32_t* idx_dtype, const void* const* dense, const int32_t* dense_dtype,
+                             float* out, int64_t ld_out, int64_t batch, int32_t n_sparse, int32_t embed_dim,
+                             int32_t n_dense, int32_t* oob_flag, void* stream) {
+  g_err[0] = 0;
+  if (!out || batch < 0 || n_sparse < 0 || n_dense < 0) { set_error("gather: bad argument"); return SWR_ERR_INVALID; }
+  std::vector<int32_t> E(n_sparse > 0 ? n_sparse : 1, embed_dim);
+  GatherLaunch g{tables, vocab, idx, idx_dtype, E.data(), dense, dense_dtype, out, ld_out, batch, n_sparse, n_dense, oob_flag};
+  return launch_gather(g, static_cast<cudaStream_t>(stream));
+}
+
+SWR_API int swr_embedding_scatter_bwd(const float* grad_out, int64_t ld_grad, int64_t batch, const void* const* idx,
+                              const int32_t* idx_dtype, float* const* grad_tables, const int64_t* vocab,
+                              int32_t n_sparse, int32_t embed_dim, void* stream) {
+  g_err[0] = 0;
+  if (!grad_out || batch < 0 || n_sparse < 0) { set_error("scatter: bad argument"); return SWR_ERR_INVALID; }
+  std::vector<int32_t> E(n_sparse > 0 ? n_sparse : 1, embed_dim);
+  ScatterLaunch s{grad_out, ld_grad, batch, idx, idx_dtype, grad_tables, vocab, E.data(), nullptr, n_sparse};
+  return launch_scatter(s, static_cast<cudaStream_t>(stream));
+}
+
+SWR_API int swr_program_run(const swr_rec_t* recs, int32_t n_recs, void* const* slots, int32_t n_slots, void* stream) {
+  g_err[0] = 0;
+  if (!recs || n_recs < 0 || !slots) { set_error("program: bad argument"); return SWR_ERR_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Ctx c{slots, n_slots, true};
+  int i = 0;
+  while (i < n_recs) {
+    const swr_rec_t& h = recs[i];
+    if (h.kind == SWR_OP_GROUP || h.n_sub < 0 || i + 1 + h.n_sub > n_recs) { set_error("program: malformed record %d (kind %d)", i, h.kind); return SWR_ERR_INVALID; }
+    const swr_rec_t* subs = recs + i + 1;
+    for (int k = 0; k < h.n_sub; ++k)
+      if (subs[k].kind != SWR_OP_GROUP) { set_error("program: record %d is not a group", i + 1 + k); return SWR_ERR_INVALID; }
+    int rc = SWR_OK;
+    switch (h.kind) {
+      case SWR_OP_ZERO: {
+        void* p = c.slot(h.s[0]);
+        const int64_t bytes = ((int64_t)(uint32_t)h.i[0]) | ((int64_t)h.i[1] << 32);
+        if (!c.ok || !p) { if (c.ok) set_error("program: zero of a null slot"); return SWR_ERR_INVALID; }
+        if (cudaMemsetAsync(p, 0, (size_t)bytes, st) != cudaSuccess) { set_error("cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError())); return SWR_ERR_CUDA; }
+        count_launch();
+        break;
+      }
+      case SWR_OP_GATHER: rc = run_gather(h, subs, c, st); break;
+      case SWR_OP_SCATTER: rc = run_scatter(h, subs, c, st); break;
+      case SWR_OP_COLSTATS:
+        rc = launch_colstats(static_cast<const float*>(c.slot(h.s[0])), h.i[0], h.i[1], h.i[2], static_cast<double*>(c.slot(h.s[1])), st);
+        break;
+      case SWR_OP_FC_FWD: case SWR_OP_FC_DGRAD: case SWR_OP_FC_WGRAD: rc = run_fc(h.kind, subs, h.n_sub, h.i[0], c, st); break;
+      case SWR_OP_POOL_FWD: rc = run_pool(h, subs, false, c, st); break;
+      case SWR_OP_POOL_BWD: rc = run_pool(h, subs, true, c, st); break;
+      case SWR_OP_HEAD_FWD: rc = run_head(h, subs, false, c, st); break;
+      case SWR_OP_HEAD_BWD: rc = run_head(h, subs, true, c, st); break;
+      case SWR_OP_BN_UPDATE: rc = run_bn(h, subs, false, c, st); break;
+      case SWR_OP_BN_PGRAD: rc = run_bn(h, subs, true, c, st); break;
+      default: set_error("program: unknown op kind %d at record %d", h.kind, i); return SWR_ERR_INVALID;
+    }
+    if (!c.ok) return SWR_ERR_INVALID;
+    if (rc) return rc;
+    i += 1 + h.n_sub;
+  }
+  return SWR_OK;
+}
+
+}  // extern "C"

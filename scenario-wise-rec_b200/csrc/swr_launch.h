@@ -1,0 +1,87 @@
+// swr_launch.h -- host-side launch descriptors shared by the kernel files and the
+// program executor (swr_exec.cu).  Everything here is plain pointers + sizes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "swr_common.cuh"
+
+namespace swr {
+
+struct GatherLaunch {
+  const float* const* tables; const int64_t* vocab; const void* const* idx; const int32_t* idx_dtype;
+  const int32_t* E;                 // per-field embed dim
+  const void* const* dense; const int32_t* dense_dtype;
+  float* out; int64_t ld; int64_t B; int n_sparse; int n_dense; int32_t* oob;
+};
+int launch_gather(const GatherLaunch& g, cudaStream_t st);
+
+struct ScatterLaunch {
+  const float* g; int64_t ld; int64_t B;
+  const void* const* idx; const int32_t* idx_dtype; float* const* gtables; const int64_t* vocab;
+  const int32_t* E; const int32_t* col;   // col may be null (fields packed in order)
+  int n_sparse;
+};
+int launch_scatter(const ScatterLaunch& s, cudaStream_t st);
+
+int launch_colstats(const float* x, int64_t B, int n, int64_t ld, double* stats, cudaStream_t st);
+
+// ---- fully-connected stack ------------------------------------------------------------
+struct FcGroup {
+  ActDev A;             // input activation (lazy)
+  ActDev Y;             // output activation: raw = Linear output, norm/act = what follows it
+  const float* W; const float* W2;        // effective weight = W (.) W2
+  const float* bias; const float* bias2;  // effective bias = bias + bias2
+  float* dW; float* dW2; float* dbias; float* dbias2;
+  double* stats_out;    // [N][2] column moments of Y (train-mode BatchNorm), or null
+  int w_layout; int ldw;
+  int e_act; float e_scale;   // epilogue activation for layers without a norm (GateNU)
+  int flags;            // bit0: A needs a gradient, bit1: accumulate into A.dz
+};
+enum { FC_A_NEEDS_GRAD = 1, FC_A_ACCUMULATE = 2 };
+
+int launch_fc_fwd(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st);
+int launch_fc_dgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st);
+int launch_fc_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st);
+
+// ---- row-local ops ----------------------------------------------------------------------
+constexpr int kMaxPoolExperts = 16;
+struct PoolGate {
+  ActDev gate;          // logits [B, nE] (BatchNorm, no activation; softmax applied here)
+  float* pooled;        // [B, ldp] plain output
+  const float* dpooled; // [B, ldp] gradient of the output
+  float* probs;         // [B, nE] saved softmax
+  int ldp; int nE;
+  int expert[kMaxPoolExperts];   // indices into the unique expert list
+};
+struct PoolLaunch {
+  const PoolGate* gates; int n_gates;
+  const ActDev* experts; int n_experts;
+  int64_t B; int H;
+};
+int launch_pool_fwd(const PoolLaunch& p, cudaStream_t st);
+int launch_pool_bwd(const PoolLaunch& p, cudaStream_t st);
+
+struct HeadDomain {
+  ActDev A;             // [B, H] lazy tower hidden (or [B,1] when w == null)
+  const float* w; const float* bias; float* dw; float* dbias;
+};
+struct HeadLaunch {
+  const HeadDomain* dom; int n_domains;
+  const void* domain_id; int dom_dtype;
+  float* out; const float* gout;           // [B]
+  const float* add; float* dadd;           // optional plain [B] added before the sigmoid (STAR aux)
+  int sig_before_select;                   // 1: select(sigmoid(v_d))   0: sigmoid(select(v_d) + add)
+  int64_t B;
+};
+int launch_head_fwd(const HeadLaunch& h, cudaStream_t st);
+int launch_head_bwd(const HeadLaunch& h, cudaStream_t st);
+
+struct BnLayer {
+  ActDev A;
+  float* rmean; float* rvar; int64_t* nbt;            // BN_UPDATE
+  float* dgamma; float* dgamma2; float* dbeta; float* dbeta2;   // BN_PGRAD
+};
+int launch_bn_update(const BnLayer* layers, int n, int64_t B, float momentum, cudaStream_t st);
+int launch_bn_pgrad(const BnLayer* layers, int n, int64_t B, cudaStream_t st);
+
+}  // namespace swr
