@@ -1,0 +1,420 @@
+"""torch-CPU interpreter of the device program records.  TEST INFRASTRUCTURE ONLY.
+
+``RefRunner`` executes the *same* ``swr_rec_t`` records the C-ABI executor
+(scenario-wise-rec_b200/csrc/swr_exec.cu) decodes, with the per-op forward and the
+hand-derived backward written out in plain torch (no autograd).  It is used
+
+* on CPU (``-m "not gpu"``): model program  ->  RefRunner  ==  reference golden vectors,
+  which checks the host-side lowering and the backward derivations without a GPU;
+* on the GPU box: every CUDA kernel is compared against the op it mirrors here.
+
+It is never imported by the product package.
+
+Record layouts follow include/swr_b200.h / DESIGN.md "Program records".
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+OP_ZERO, OP_GATHER, OP_SCATTER, OP_COLSTATS = 1, 2, 3, 4
+OP_FC_FWD, OP_FC_DGRAD, OP_FC_WGRAD = 5, 6, 7
+OP_POOL_FWD, OP_POOL_BWD, OP_HEAD_FWD, OP_HEAD_BWD = 8, 9, 10, 11
+OP_BN_UPDATE, OP_BN_PGRAD, OP_NORM_BWD, OP_GROUP = 12, 13, 14, 100
+NORM_NONE, NORM_BATCH, NORM_RUNNING = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_LEAKY = 0, 1, 2, 3
+
+
+def act_fwd(z, act):
+    if act == ACT_RELU:
+        return torch.relu(z)
+    if act == ACT_SIGMOID:
+        return torch.sigmoid(z)
+    if act == ACT_LEAKY:
+        return torch.where(z > 0, z, 0.1 * z)
+    return z
+
+
+def act_grad(z, act):
+    if act == ACT_RELU:
+        return (z > 0).to(z.dtype)
+    if act == ACT_SIGMOID:
+        a = torch.sigmoid(z)
+        return a * (1 - a)
+    if act == ACT_LEAKY:
+        return torch.where(z > 0, torch.ones_like(z), torch.full_like(z, 0.1))
+    return torch.ones_like(z)
+
+
+class _Act:
+    """Decoded ActRef: tensors are [B, n] views into the slot storage."""
+
+    def __init__(self, run, rec, sb, ib, fb):
+        s, i, f = rec["s"], rec["i"], rec["f"]
+        self.ld, self.n, self.mode, self.act = int(i[ib]), int(i[ib + 1]), int(i[ib + 2]), int(i[ib + 3])
+        self.eps = float(f[fb])
+        B = run.prog.B
+        v2 = lambda slot: None if slot < 0 else run.slot(slot)[:B * self.ld].view(B, self.ld)[:, :self.n]   # noqa: E731
+        v1 = lambda slot: None if slot < 0 else run.slot(slot).reshape(-1)[:self.n]                           # noqa: E731
+        self.raw = v2(int(s[sb]))
+        self.stats = None if s[sb + 1] < 0 else run.slot(int(s[sb + 1]))[:2 * self.n].view(self.n, 2)
+        self.rmean, self.rvar = v1(int(s[sb + 2])), v1(int(s[sb + 3]))
+        self.gamma, self.gamma2 = v1(int(s[sb + 4])), v1(int(s[sb + 5]))
+        self.beta, self.beta2 = v1(int(s[sb + 6])), v1(int(s[sb + 7]))
+        self.dz = v2(int(s[sb + 8]))
+        self.dstats = None if s[sb + 9] < 0 else run.slot(int(s[sb + 9]))[:2 * self.n].view(self.n, 2)
+        self.B = B
+
+    # per-column coefficients (csrc/swr_common.cuh col_coef)
+    def coef(self):
+        n = self.n
+        if self.mode == NORM_NONE:
+            z = torch.zeros(n)
+            return z, torch.ones(n), z.clone(), torch.ones(n)
+        if self.mode == NORM_BATCH:
+            mu = self.stats[:, 0] / self.B
+            var = (self.stats[:, 1] / self.B - mu * mu).clamp_min(0.0)
+        else:
+            mu, var = self.rmean.double(), self.rvar.double()
+        r = (1.0 / torch.sqrt(var + self.eps)).float()
+        g = torch.ones(n)
+        if self.gamma is not None:
+            g = g * self.gamma
+        if self.gamma2 is not None:
+            g = g * self.gamma2
+        b = torch.zeros(n)
+        if self.beta is not None:
+            b = b + self.beta
+        if self.beta2 is not None:
+            b = b + self.beta2
+        return mu.float(), g * r, b, r
+
+    def z(self):
+        mu, s, b, _ = self.coef()
+        return (self.raw - mu) * s + b
+
+    def value(self):
+        return act_fwd(self.z(), self.act)
+
+    def xhat(self):
+        mu, _, _, r = self.coef()
+        return (self.raw - mu) * r
+
+    def write_grad(self, dA, accumulate=False):
+        """stage 1: dz = dA * act'(z); accumulate the column sums used by stage 2 / d gamma, d beta."""
+        plain = self.mode == NORM_NONE and self.act == ACT_NONE
+        dz = dA if plain else dA * act_grad(self.z(), self.act)
+        if self.mode != NORM_NONE and self.dstats is not None:
+            self.dstats[:, 0] += dz.double().sum(0)
+            self.dstats[:, 1] += (dz.double() * self.xhat().double()).sum(0)
+        if self.dz is not None:
+            if accumulate:
+                self.dz += dz
+            else:
+                self.dz.copy_(dz)
+
+    def dy(self):
+        """stage 2: gradient wrt the raw tensor from dz (csrc/swr_common.cuh dy_coef)."""
+        if self.mode == NORM_NONE:
+            return self.dz
+        mu, s, _, r = self.coef()
+        if self.mode == NORM_RUNNING:
+            return self.dz * s
+        S1, S2 = self.dstats[:, 0], self.dstats[:, 1]
+        sd, rd, mud, ib = s.double(), r.double(), mu.double(), 1.0 / self.B
+        c1 = (-sd * rd * S2 * ib).float()
+        c2 = (-sd * S1 * ib + sd * rd * S2 * mud * ib).float()
+        return s * self.dz + c1 * self.raw + c2
+
+
+class RefRunner:
+    """Drop-in for program.CudaRunner on CPU tensors."""
+
+    def __init__(self, prog):
+        self.prog = prog
+        self.ws32 = torch.zeros(max(prog.ws32, 1), dtype=torch.float32)
+        self.ws64 = torch.zeros(max(prog.ws64, 1), dtype=torch.float64)
+        self.oob = torch.zeros(2, dtype=torch.int32)
+        self.tensors = [None] * len(prog.slot_desc)
+        for i, d in enumerate(prog.slot_desc):
+            if d[0] == "static":
+                self.tensors[i] = d[1].detach()
+            elif d[0] == "ws32":
+                self.tensors[i] = self.ws32[d[1]:d[1] + d[2]]
+            elif d[0] == "ws64":
+                self.tensors[i] = self.ws64[d[1]:d[1] + d[2]]
+            elif d[0] == "special":
+                self.tensors[i] = self.oob
+        self.generation = 0
+
+    def slot(self, i):
+        t = self.tensors[i]
+        assert t is not None, f"slot {i} ({self.prog.slot_desc[i][:2]}) is unbound"
+        return t
+
+    # ---- public API (mirrors CudaRunner) ------------------------------------------------
+    def check_indices(self):
+        if int(self.oob[0]) != 0:
+            f = int(self.oob[1])
+            self.oob.zero_()
+            raise IndexError(f"index out of range in self (sparse field #{f})")
+
+    def forward(self, x):
+        for name, slot in self.prog.inputs.items():
+            if name != "__grad_out__":
+                self.tensors[slot] = x[name]
+        self._run(self.prog.recs_fwd)
+        self.generation += 1
+        outs = []
+        if self.prog.out_slot >= 0:
+            o = self.prog.slot_desc[self.prog.out_slot]
+            outs.append(self.ws32[o[1]:o[1] + self.prog.B].clone())
+        for raw, ld, n, _dz in self.prog.outputs:
+            outs.append(self._view(raw, ld, n).clone())
+        return tuple(outs)
+
+    def _view(self, slot, ld, n):
+        B = self.prog.B
+        return self.slot(slot)[:B * ld].view(B, ld)[:, :n]
+
+    def backward(self, gouts):
+        prog = self.prog
+        gouts = list(gouts)
+        arenas = {k: torch.zeros(max(v, 1), dtype=torch.float32) for k, v in prog.arena_size.items()}
+        for i, d in enumerate(prog.slot_desc):
+            if d[0] == "grad":
+                self.tensors[i] = arenas[d[1]][d[2]:d[2] + d[3]]
+        if prog.out_slot >= 0:
+            g = gouts.pop(0)
+            self.tensors[prog.gout_slot] = torch.zeros(prog.B) if g is None else g.contiguous()
+        for (raw, ld, n, dz), g in zip(prog.outputs, gouts):
+            if dz >= 0:
+                v = self._view(dz, ld, n)
+                v.zero_() if g is None else v.copy_(g)
+        self._run(prog.recs_bwd)
+        return [arenas[a][off:off + n].view(p.shape) for p, (a, off, n) in zip(prog.params, prog.param_arena)]
+
+    # ---- interpreter ------------------------------------------------------------------------
+    def _run(self, recs):
+        i = 0
+        while i < len(recs):
+            h = recs[i]
+            subs = recs[i + 1:i + 1 + int(h["n_sub"])]
+            assert int(h["kind"]) != OP_GROUP and all(int(r["kind"]) == OP_GROUP for r in subs)
+            getattr(self, "_op_%d" % int(h["kind"]))(h, subs)
+            i += 1 + int(h["n_sub"])
+
+    @staticmethod
+    def _i64(lo, hi):
+        return (int(lo) & 0xFFFFFFFF) | (int(hi) << 32)
+
+    def _op_1(self, h, subs):       # ZERO
+        t = self.slot(int(h["s"][0]))
+        nbytes = self._i64(h["i"][0], h["i"][1])
+        base = self.ws64 if t.dtype == torch.float64 else self.ws32
+        off = t.storage_offset()
+        base[off:off + nbytes // t.element_size()].zero_()
+
+    def _op_2(self, h, subs):       # GATHER
+        B, ld = int(h["i"][0]), int(h["i"][4])
+        out = self.slot(int(h["s"][0]))[:B * ld].view(B, ld)
+        for f, r in enumerate(subs):
+            col = int(r["i"][3])
+            if int(r["i"][4]) == 0:
+                tab = self.slot(int(r["s"][0]))
+                idx = self.slot(int(r["s"][1])).long()
+                vocab, E = self._i64(r["i"][0], r["i"][1]), int(r["i"][5])
+                bad = (idx < 0) | (idx >= vocab)
+                if bool(bad.any()):
+                    self.oob[0], self.oob[1] = 1, f
+                rows = tab[idx.clamp(0, vocab - 1)]
+                rows = torch.where(bad.unsqueeze(1), torch.zeros_like(rows), rows)
+                out[:, col:col + E] = rows
+            else:
+                out[:, col] = self.slot(int(r["s"][0])).float()
+
+    def _op_3(self, h, subs):       # SCATTER
+        B, ld = int(h["i"][0]), int(h["i"][4])
+        g = self.slot(int(h["s"][0]))[:B * ld].view(B, ld)
+        for r in subs:
+            vocab, E, col = self._i64(r["i"][0], r["i"][1]), int(r["i"][5]), int(r["i"][3])
+            gt = self.slot(int(r["s"][0]))[:vocab * E].view(vocab, E)
+            idx = self.slot(int(r["s"][1])).long()
+            ok = (idx >= 0) & (idx < vocab)
+            gt.index_add_(0, idx[ok], g[ok, col:col + E])
+
+    def _op_4(self, h, subs):       # COLSTATS
+        B, n, ld = int(h["i"][0]), int(h["i"][1]), int(h["i"][2])
+        x = self.slot(int(h["s"][0]))[:B * ld].view(B, ld)[:, :n].double()
+        st = self.slot(int(h["s"][1]))[:2 * n].view(n, 2)
+        st[:, 0] += x.sum(0)
+        st[:, 1] += (x * x).sum(0)
+
+    # -- fully connected ---------------------------------------------------------------------
+    def _weff(self, r):
+        s = r["s"]
+        W = self.slot(int(s[24]))
+        if s[25] >= 0:
+            W = W * self.slot(int(s[25]))
+        if int(r["i"][8]) == 1:      # KN -> [N, K]
+            W = W.t()
+        return W
+
+    def _op_5(self, h, subs):       # FC_FWD
+        for r in subs:
+            A, Y = _Act(self, r, 0, 0, 0), _Act(self, r, 12, 4, 2)
+            s = r["s"]
+            y = A.value() @ self._weff(r).t()
+            if s[26] >= 0:
+                y = y + self.slot(int(s[26]))
+            if s[27] >= 0:
+                y = y + self.slot(int(s[27]))
+            if int(r["i"][10]) != ACT_NONE:
+                y = act_fwd(y, int(r["i"][10])) * float(r["f"][4])
+            Y.raw.copy_(y)
+            if Y.mode == NORM_BATCH:
+                Y.stats[:, 0] += y.double().sum(0)
+                Y.stats[:, 1] += (y.double() ** 2).sum(0)
+
+    def _op_6(self, h, subs):       # FC_DGRAD (fan-in)
+        dA = None
+        for r in subs:
+            Y = _Act(self, r, 12, 4, 2)
+            t = Y.dy() @ self._weff(r)
+            dA = t if dA is None else dA + t
+        D = _Act(self, subs[0], 0, 0, 0)
+        D.write_grad(dA, accumulate=bool(int(subs[0]["i"][11]) & 2))
+
+    def _op_7(self, h, subs):       # FC_WGRAD
+        for r in subs:
+            A, Y = _Act(self, r, 0, 0, 0), _Act(self, r, 12, 4, 2)
+            s = r["s"]
+            dy = Y.dy()
+            dW = dy.t() @ A.value()                     # [N, K]
+            kn = int(r["i"][8]) == 1
+            if kn:
+                dW = dW.t()
+            W, W2 = self.slot(int(s[24])), (self.slot(int(s[25])) if s[25] >= 0 else None)
+            if W2 is not None:
+                if s[28] >= 0:
+                    self.slot(int(s[28])).view(W.shape).add_(dW * W2)
+                if s[29] >= 0:
+                    self.slot(int(s[29])).view(W.shape).add_(dW * W)
+            elif s[28] >= 0:
+                self.slot(int(s[28])).view(W.shape).add_(dW)
+            db = dy.sum(0)
+            if s[30] >= 0:
+                self.slot(int(s[30])).add_(db)
+            if s[31] >= 0:
+                self.slot(int(s[31])).add_(db)
+
+    # -- pooling -------------------------------------------------------------------------------
+    def _pool_decode(self, h, subs):
+        ng, ne = int(h["i"][2]), int(h["i"][3])
+        gates = []
+        for r in subs[:ng]:
+            nE = int(r["i"][8])
+            gate, out = _Act(self, r, 0, 0, 0), _Act(self, r, 12, 4, 2)
+            probs = self.slot(int(r["s"][24]))[:self.prog.B * nE].view(self.prog.B, nE)
+            gates.append((gate, out, probs, [int(v) for v in r["i"][16:16 + nE]]))
+        experts = [_Act(self, r, 0, 0, 0) for r in subs[ng:ng + ne]]
+        return gates, experts
+
+    def _op_8(self, h, subs):       # POOL_FWD
+        gates, experts = self._pool_decode(h, subs)
+        vals = [e.value() for e in experts]
+        for gate, out, probs, idx in gates:
+            p = torch.softmax(gate.z(), dim=1)
+            probs.copy_(p)
+            out.raw.copy_(sum(p[:, e:e + 1] * vals[u] for e, u in enumerate(idx)))
+
+    def _op_9(self, h, subs):       # POOL_BWD
+        gates, experts = self._pool_decode(h, subs)
+        vals = [e.value() for e in experts]
+        dA = [torch.zeros_like(v) for v in vals]
+        for gate, out, probs, idx in gates:
+            dP = out.dz
+            dp = torch.stack([(dP * vals[u]).sum(1) for u in idx], dim=1)
+            dot = (probs * dp).sum(1, keepdim=True)
+            gate.write_grad(probs * (dp - dot))          # gate act is NONE: dz = d logits
+            for e, u in enumerate(idx):
+                dA[u] += probs[:, e:e + 1] * dP
+        for e, d in zip(experts, dA):
+            e.write_grad(d)
+
+    # -- head -----------------------------------------------------------------------------------
+    def _op_10(self, h, subs):      # HEAD_FWD
+        B = self.prog.B
+        dom = self.slot(int(h["s"][0])).long()
+        out = self.slot(int(h["s"][1]))[:B]
+        sbs = int(h["i"][2]) == 1
+        v = torch.zeros(B)
+        sel_any = torch.zeros(B, dtype=torch.bool)
+        for d, r in enumerate(subs):
+            A = _Act(self, r, 0, 0, 0)
+            a = A.value()
+            if r["s"][24] >= 0:
+                vd = a @ self.slot(int(r["s"][24])).reshape(-1)
+                if r["s"][26] >= 0:
+                    vd = vd + self.slot(int(r["s"][26])).reshape(-1)[0]
+            else:
+                vd = a[:, 0]
+            m = dom == d
+            v = torch.where(m, vd, v)
+            sel_any |= m
+        if sbs:
+            out.copy_(torch.where(sel_any, torch.sigmoid(v), torch.zeros(B)))
+        else:
+            add = self.slot(int(h["s"][3]))[:B] if h["s"][3] >= 0 else 0.0
+            out.copy_(torch.sigmoid(v + add))
+
+    def _op_11(self, h, subs):      # HEAD_BWD
+        B = self.prog.B
+        dom = self.slot(int(h["s"][0])).long()
+        y = self.slot(int(h["s"][1]))[:B]
+        g = self.slot(int(h["s"][2]))[:B]
+        sbs = int(h["i"][2]) == 1
+        dsig = g * y * (1 - y)
+        if not sbs and h["s"][4] >= 0:
+            self.slot(int(h["s"][4]))[:B].copy_(dsig)
+        for d, r in enumerate(subs):
+            A = _Act(self, r, 0, 0, 0)
+            dv = torch.where(dom == d, dsig, torch.zeros(B))
+            if r["s"][24] >= 0:
+                w = self.slot(int(r["s"][24])).reshape(-1)
+                if r["s"][28] >= 0:
+                    self.slot(int(r["s"][28])).reshape(-1).add_(dv @ A.value())
+                if r["s"][30] >= 0:
+                    self.slot(int(r["s"][30])).reshape(-1)[0] += dv.sum()
+                dA = dv.unsqueeze(1) * w.unsqueeze(0)
+            else:
+                dA = dv.unsqueeze(1)
+            A.write_grad(dA)
+
+    # -- batch-norm bookkeeping ----------------------------------------------------------------------
+    def _op_12(self, h, subs):      # BN_UPDATE
+        B, m = self.prog.B, float(h["f"][4])
+        for r in subs:
+            A = _Act(self, r, 0, 0, 0)
+            mu = A.stats[:, 0] / B
+            var = (A.stats[:, 1] / B - mu * mu).clamp_min(0.0) * (B / (B - 1) if B > 1 else 1.0)
+            A.rmean.copy_((1 - m) * A.rmean + m * mu.float())
+            A.rvar.copy_((1 - m) * A.rvar + m * var.float())
+            if r["s"][24] >= 0:
+                self.slot(int(r["s"][24])).add_(1)
+
+    def _op_13(self, h, subs):      # BN_PGRAD
+        for r in subs:
+            A = _Act(self, r, 0, 0, 0)
+            s1, s2 = A.dstats[:, 0].float(), A.dstats[:, 1].float()
+            g1 = A.gamma if A.gamma is not None else torch.ones(A.n)
+            g2 = A.gamma2 if A.gamma2 is not None else torch.ones(A.n)
+            s = r["s"]
+            if s[24] >= 0:
+                self.slot(int(s[24])).add_(s2 * g2)
+            if s[25] >= 0:
+                self.slot(int(s[25])).add_(s2 * g1)
+            if s[26] >= 0:
+                self.slot(int(s[26])).add_(s1)
+            if s[27] >= 0:
+                self.slot(int(s[27])).add_(s1)

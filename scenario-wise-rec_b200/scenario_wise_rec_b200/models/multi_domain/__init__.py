@@ -1,0 +1,6 @@
+"""Drop-in multi-domain models (reference: scenario_wise_rec/models/multi_domain/__init__.py)."""
+from .sharebottom import SharedBottom
+from .mmoe import MMOE
+from .ple import PLE
+
+__all__ = ["SharedBottom", "MMOE", "PLE"]
