@@ -91,6 +91,7 @@ class Program:
     gout_slot: int = -1
     oob_slot: int = -1
     outputs: List[Tuple[int, int, int, int]] = field(default_factory=list)   # plain [B, n] outputs: (raw slot, ld, n, dz slot)
+    labels: Dict[int, str] = field(default_factory=dict)
     n_launch_fwd: int = 0
     n_launch_bwd: int = 0
 
@@ -115,6 +116,8 @@ class ProgramBuilder:
         self.out_slot = self.gout_slot = self.oob_slot = -1
         self._stats_slots: List[int] = []
         self._outputs: List[Act] = []
+        self.labels: Dict[int, str] = {}     # debug names of workspace slots (tests compare them one by one)
+        self._n_acts = 0
 
     # ---- slots ------------------------------------------------------------------------
     def _new_slot(self, desc) -> int:
@@ -161,12 +164,16 @@ class ProgramBuilder:
                 ld: Optional[int] = None) -> Act:
         ld = _round_up(n, 4) if ld is None else ld
         a = Act(self.ws(self.B * ld) if raw is None else raw, ld, n, norm, act)
+        a.name = f"a{self._n_acts}[{n}]"
+        self._n_acts += 1
+        self.labels.setdefault(a.raw, a.name + ".raw")
         if norm is not None:
             has_running = norm.rmean is not None and norm.rvar is not None
             a.mode = N.NORM_BATCH if (self.training or norm.always_batch or not has_running) else N.NORM_RUNNING
             if a.mode == N.NORM_BATCH:
                 a.stats = self.ws(2 * n, f64=True)
                 self._stats_slots.append(a.stats)
+                self.labels[a.stats] = a.name + ".stats"
             a.nslots = {k: self.static(getattr(norm, k)) for k in ("gamma", "gamma2", "beta", "beta2", "rmean", "rvar")}
             self.norm_acts.append(a)
         return a
@@ -175,6 +182,7 @@ class ProgramBuilder:
         if a.dz < 0:
             a.dz = self.ws(self.B * a.ld)
             a.needs_grad = True
+            self.labels[a.dz] = a.name + ".dz"
 
     # ---- forward ops ------------------------------------------------------------------
     def gather(self, sparse: Sequence[Tuple[str, torch.Tensor]], dense: Sequence[str],
@@ -229,6 +237,7 @@ class ProgramBuilder:
                 idx.append(experts.index(e))
             out = self.new_act(H)
             probs = self.ws(self.B * gate.n)
+            self.labels[probs] = out.name + ".probs"
             entries.append((gate, idx, out, probs))
         self.tape.append(("pool", entries, experts, H))
         return [e[2] for e in entries]
@@ -236,6 +245,7 @@ class ProgramBuilder:
     def head(self, domains: Sequence[Tuple[Act, Optional[torch.Tensor], Optional[torch.Tensor]]],
              dom_dtype: torch.dtype, sig_before_select: bool = True, add: Optional[Act] = None) -> int:
         self.out_slot = self.ws(self.B)
+        self.labels[self.out_slot] = "head.out"
         self.gout_slot = self.input("__grad_out__")
         self.tape.append(("head", list(domains), dom_dtype, sig_before_select, add))
         return self.out_slot
@@ -329,6 +339,7 @@ class ProgramBuilder:
         for a in self.norm_acts:
             if a.needs_grad:
                 a.dstats = self.ws(2 * a.n, f64=True)
+                self.labels[a.dstats] = a.name + ".dstats"
 
         # forward statistics region is contiguous in the f64 arena by construction? not necessarily:
         # zero each statistics buffer range as one span from the first to the last stats slot.
@@ -532,6 +543,7 @@ class ProgramBuilder:
                        params=self.params, param_arena=self.param_arena, arena_size=dict(self.arena_size),
                        out_slot=self.out_slot, gout_slot=self.gout_slot, oob_slot=self.oob_slot,
                        outputs=[(a.raw, a.ld, a.n, a.dz if a.needs_grad else -1) for a in self._outputs],
+                       labels=dict(self.labels),
                        n_launch_fwd=launches(fwd), n_launch_bwd=launches(bwd))
 
 

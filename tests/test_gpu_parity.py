@@ -1,0 +1,262 @@
+"""-m gpu: the CUDA path (through the C ABI) against the oracle.
+
+* golden fixtures (outputs / gradients / BN buffers generated from the unmodified reference),
+* op-by-op: every workspace buffer of the device program vs the torch-CPU interpreter,
+* BASELINE.json shapes (cfg1..cfg3) vs oracle/ref_models.py run live on the host,
+* size-independent properties at large sizes (gather bit-exactness, scatter conservation).
+Tolerances: gather / indices bit-exact; outputs 1e-4 abs fp32 (north_star); gradients absolute,
+relative to max|grad| of the tensor (a bias feeding BatchNorm has an analytically zero gradient).
+"""
+import copy
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import Golden, golden_names
+import gpu_util
+import model_factory
+from oracle import ref_models
+from oracle.ops_ref import RefRunner
+from scenario_wise_rec_b200 import _native as N
+from scenario_wise_rec_b200.program import CudaRunner
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_library_loads_on_device():
+    assert N.lib().swr_abi_version() == N.ABI_VERSION
+    assert N.lib().swr_device_check() == 0, N.last_error()
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden(name):
+    g = Golden(name)
+    if not model_factory.supported(g.model):
+        pytest.skip(f"{g.model} not lowered yet")
+    model = model_factory.build(g.model, g.cfg)
+    model.load_state_dict(g.state0)
+    model.to(DEV)
+    before = N.launch_count()
+    model_factory.check_against_golden(model, g, device=DEV)
+    assert N.launch_count() > before, "no kernel of libswr_b200.so was launched"
+
+
+@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("training", [True, False])
+def test_every_buffer_matches_interpreter(name, training):
+    """Runs the same records on both executors and compares every activation, statistic,
+    gradient buffer and parameter gradient."""
+    g = Golden(name)
+    if not model_factory.supported(g.model):
+        pytest.skip(f"{g.model} not lowered yet")
+    model = model_factory.build(g.model, g.cfg)
+    model.load_state_dict(g.state0)
+    model.train(training)
+    model_ref = copy.deepcopy(model)
+    model.to(DEV)
+    xg = {k: v.to(DEV) for k, v in g.x.items()}
+    rc = model._runner(xg)
+    rr = RefRunner(_prog(model_ref, g.x))
+    oc = rc.forward(xg)
+    orf = rr.forward(g.x)
+    torch.cuda.synchronize()
+    report = []
+    fails = gpu_util.compare_slots(rc, rr, [".raw", ".stats", ".probs", "head.out"], report=report)
+    assert not fails, f"forward buffers differ: {fails[:5]}"
+    gout = torch.linspace(-1, 1, g.B)
+    gc = rc.backward([gout.to(DEV)] + [None] * (len(oc) - 1))
+    gr = rr.backward([gout] + [None] * (len(orf) - 1))
+    torch.cuda.synchronize()
+    fails = gpu_util.compare_slots(rc, rr, [".dz", ".dstats"], atol=1e-5, rtol=2e-4)
+    assert not fails, f"backward buffers differ: {fails[:5]}"
+    for p, a, b in zip(rc.prog.params, gc, gr):
+        scale = max(float(b.abs().max()), 1e-3)
+        err = float((a.cpu() - b).abs().max())
+        assert err <= 2e-4 * scale, f"param grad {tuple(p.shape)} err {err} scale {scale}"
+
+
+def _prog(model, x):
+    from scenario_wise_rec_b200.program import ProgramBuilder
+    cols = model._columns()
+    b = ProgramBuilder(int(x[cols[0]].shape[0]), model.training)
+    model._lower(b, {c: x[c].dtype for c in cols})
+    return b.finish()
+
+
+# --------------------------------------------------------------------------------------------
+# BASELINE.json shapes against the oracle run live on the host cores
+# --------------------------------------------------------------------------------------------
+ALI_VOCAB = [238635, 98, 14, 3, 8, 4, 4, 3, 5, 467298, 6929, 263942, 80232, 106399, 5888, 104830, 51878, 37148,
+             3, 5853, 105622, 53843, 31858]
+
+
+def ali_ccp_features(scale=1):
+    f = [(f"D{i}", "dense", 0, 1) for i in range(8)]
+    f += [(f"s{i}", "sparse", max(2, v // scale), 16) for i, v in enumerate(ALI_VOCAB)]
+    return f
+
+
+def kuairand_features():
+    vocab = [4_000_000 // 8, 1000] + [50 + 45 * i for i in range(30)]
+    return [(f"s{i}", "sparse", v, 16) for i, v in enumerate(vocab)] + [(f"D{i}", "dense", 0, 1) for i in range(4)]
+
+
+def ml1m_features():
+    return [("user_id", "sparse", 6041, 16), ("movie_id", "sparse", 3953, 16), ("gender", "sparse", 3, 16),
+            ("age", "sparse", 8, 16), ("occupation", "sparse", 22, 16), ("zip", "sparse", 3440, 16), ("d0", "dense", 0, 1)]
+
+
+BASELINE_CASES = {
+    "cfg1_sharedbottom_ml1m_b256": ("SharedBottom", dict(features=ml1m_features(), domain_num=3, bottom_dims=[128], tower_dims=[8]), 256),
+    "cfg2_mmoe_aliccp_b4096": ("MMOE", dict(features=ali_ccp_features(), domain_num=3, n_expert=4,
+                                            expert_dims=[256, 128, 64, 32, 16, 8], tower_dims=[16]), 4096),
+    "cfg3_ple_kuairand_b8192": ("PLE", dict(features=kuairand_features(), domain_num=5, n_level=1, n_expert_specific=2,
+                                            n_expert_shared=2, expert_dims=[64, 32], tower_dims=[16]), 8192),
+}
+
+
+@pytest.mark.parametrize("case", sorted(BASELINE_CASES))
+def test_baseline_shapes_vs_oracle(case):
+    model_name, cfg, B = BASELINE_CASES[case]
+    if not model_factory.supported(model_name):
+        pytest.skip(f"{model_name} not lowered yet")
+    torch.manual_seed(7)
+    model = model_factory.build(model_name, cfg)
+    gpu_util.randomise(model, 11)
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    x, y = gpu_util.make_batch(cfg["features"], B, cfg["domain_num"], seed=5, zipf=True)
+    # oracle on the host
+    st = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running_" not in k else v.clone())
+          for k, v in state.items()}
+    bn_out = {}
+    ref = ref_models.forward(model_name, x, st, cfg, training=True, bn_out=bn_out)
+    ref_models.bce_loss(ref, y).backward()
+    # CUDA path
+    model.to(DEV).train()
+    out = model({k: v.to(DEV) for k, v in x.items()})
+    torch.nn.BCELoss()(out, y.to(DEV)).backward()
+    err = float((out.detach().cpu() - ref.detach()).abs().max())
+    assert err <= 1e-4, f"output err {err}"
+    worst = ("", 0.0)
+    for k, p in model.named_parameters():
+        r = st[k].grad
+        assert (r is None) == (p.grad is None), k
+        if r is None:
+            continue
+        scale = max(float(r.abs().max()), 1e-3 * float(max(abs(float(ref_models.bce_loss(ref, y).detach())), 1.0)))
+        e = float((p.grad.cpu() - r).abs().max()) / scale
+        worst = max(worst, (k, e), key=lambda t: t[1])
+    assert worst[1] <= 5e-4, f"gradient {worst}"
+    sd = model.state_dict()
+    for k, v in bn_out.items():
+        torch.testing.assert_close(sd[k].cpu().to(v.dtype), v, atol=2e-5, rtol=1e-4)
+    # eval mode
+    model.load_state_dict(state)
+    model.eval()
+    with torch.no_grad():
+        oe = model({k: v.to(DEV) for k, v in x.items()})
+        re = ref_models.forward(model_name, x, state, cfg, training=False)
+    assert float((oe.cpu() - re).abs().max()) <= 1e-4
+
+
+# --------------------------------------------------------------------------------------------
+# K1 / K2 through the raw C ABI
+# --------------------------------------------------------------------------------------------
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def _gather_abi(tables, idx, dense, B, E):
+    out = torch.empty(B, len(tables) * E + len(dense), device=DEV)
+    vocab = (ctypes.c_int64 * len(tables))(*[t.shape[0] for t in tables])
+    idt = (ctypes.c_int32 * len(idx))(*[N.torch_dtype_code(t.dtype) for t in idx])
+    ddt = (ctypes.c_int32 * max(len(dense), 1))(*[N.torch_dtype_code(t.dtype) for t in dense])
+    oob = torch.zeros(2, dtype=torch.int32, device=DEV)
+    st = N.lib().swr_embedding_gather_fwd(_ptr_array(tables), vocab, _ptr_array(idx), idt, _ptr_array(dense) if dense else None,
+                                          ddt, out.data_ptr(), out.shape[1], B, len(tables), E, len(dense), oob.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream)
+    N.check(st, "gather")
+    return out, oob
+
+
+@pytest.mark.parametrize("B,E", [(1, 16), (37, 16), (4096, 16), (1000, 64), (513, 6)])
+def test_gather_bit_exact(B, E):
+    g = torch.Generator().manual_seed(B + E)
+    vocabs = [7, 300, 5000, 3, 12345]
+    tables = [torch.randn(v, E, generator=g).to(DEV) for v in vocabs]
+    dts = [torch.int64, torch.int32, torch.int16, torch.int8, torch.int64]
+    idx = [torch.randint(0, min(v, 127 if dt == torch.int8 else v), (B,), generator=g).to(dt).to(DEV) for v, dt in zip(vocabs, dts)]
+    dense = [torch.rand(B, generator=g).to(DEV), torch.rand(B, generator=g).half().to(DEV), torch.rand(B, generator=g).double().to(DEV)]
+    out, oob = _gather_abi(tables, idx, dense, B, E)
+    ref = torch.cat([t[i.long()] for t, i in zip(tables, idx)] + [d.float().unsqueeze(1) for d in dense], dim=1)
+    assert torch.equal(out, ref)          # a gather is a copy: bit-exact
+    assert int(oob[0]) == 0
+
+
+def test_gather_out_of_range_flag():
+    tables = [torch.randn(10, 16, device=DEV), torch.randn(5, 16, device=DEV)]
+    idx = [torch.tensor([1, 2, 3], device=DEV), torch.tensor([0, 5, -1], device=DEV)]
+    out, oob = _gather_abi(tables, idx, [], 3, 16)
+    assert int(oob[0]) == 1 and int(oob[1]) == 1
+    assert torch.equal(out[1, 16:], torch.zeros(16, device=DEV))
+    assert torch.equal(out[0, 16:], tables[1][0])
+
+
+@pytest.mark.parametrize("B,E,vocabs", [(4096, 16, [3, 40, 5000, 200000]), (8192, 64, [20, 748000]), (100, 6, [9, 50])])
+def test_scatter_matches_index_add(B, E, vocabs):
+    g = torch.Generator().manual_seed(B)
+    idx = [(v * torch.rand(B, generator=g) ** 3).long().clamp_(0, v - 1).to(DEV) for v in vocabs]   # skewed: hot rows
+    grad = torch.randn(B, len(vocabs) * E, generator=g).to(DEV)
+    gt = [torch.zeros(v, E, device=DEV) for v in vocabs]
+    vocab = (ctypes.c_int64 * len(vocabs))(*vocabs)
+    idt = (ctypes.c_int32 * len(idx))(*[N.DT_I64] * len(idx))
+    st = N.lib().swr_embedding_scatter_bwd(grad.data_ptr(), grad.shape[1], B, _ptr_array(idx), idt, _ptr_array(gt), vocab,
+                                           len(vocabs), E, torch.cuda.current_stream().cuda_stream)
+    N.check(st, "scatter")
+    for f, v in enumerate(vocabs):
+        ref = torch.zeros(v, E, dtype=torch.float64, device=DEV).index_add_(0, idx[f], grad[:, f * E:(f + 1) * E].double())
+        # fp32 atomics reorder the sums: tolerance ~ eps * count * |g|
+        torch.testing.assert_close(gt[f].double(), ref, atol=2e-4, rtol=1e-5)
+    # conservation (size-independent property): total mass is preserved per field
+    for f in range(len(vocabs)):
+        assert abs(float(gt[f].double().sum() - grad[:, f * E:(f + 1) * E].double().sum())) < 1e-2
+
+
+def test_gather_scatter_large_roundtrip():
+    """2^22 lookups: gather is bit-exact; scatter of the gathered rows' all-ones gradient counts occurrences."""
+    B, E, V = 1 << 22, 16, 1 << 20
+    g = torch.Generator().manual_seed(3)
+    table = torch.randn(V, E, generator=g).to(DEV)
+    idx = torch.randint(0, V, (B,), generator=g).to(DEV)
+    out, _ = _gather_abi([table], [idx], [], B, E)
+    assert torch.equal(out, table[idx])
+    gt = torch.zeros(V, E, device=DEV)
+    ones = torch.ones(B, E, device=DEV)
+    vocab = (ctypes.c_int64 * 1)(V)
+    idt = (ctypes.c_int32 * 1)(N.DT_I64)
+    N.check(N.lib().swr_embedding_scatter_bwd(ones.data_ptr(), E, B, _ptr_array([idx]), idt, _ptr_array([gt]), vocab, 1, E,
+                                               torch.cuda.current_stream().cuda_stream), "scatter")
+    counts = torch.bincount(idx, minlength=V).float()
+    assert torch.equal(gt[:, 0], counts) and torch.equal(gt[:, E - 1], counts)   # small integers: exact in fp32
+
+
+def test_embedding_layer_standalone():
+    from scenario_wise_rec_b200.basic.layers import EmbeddingLayer
+    feats = model_factory.features([("a", "sparse", 11, 8), ("d", "dense", 0, 1), ("b", "sparse", 5, 8)])
+    emb = EmbeddingLayer(feats).to(DEV)
+    x = {"a": torch.tensor([0, 10, 3], device=DEV), "b": torch.tensor([4, 4, 1], device=DEV), "d": torch.tensor([.5, .25, 1.], device=DEV)}
+    out = emb(x, feats, squeeze_dim=True)
+    ref = torch.cat([emb.embed_dict["a"].weight[x["a"]], emb.embed_dict["b"].weight[x["b"]], x["d"].unsqueeze(1)], 1)
+    assert torch.equal(out.detach(), ref.detach())
+    out.sum().backward()
+    ga = torch.zeros(11, 8, device=DEV).index_add_(0, x["a"], torch.ones(3, 8, device=DEV))
+    assert torch.equal(emb.embed_dict["a"].weight.grad, ga)
+    out3 = emb(x, feats, squeeze_dim=False)
+    assert out3.shape == (3, 2, 8)
+    x["a"] = torch.tensor([0, 11, 3], device=DEV)
+    emb(x, feats, squeeze_dim=True)
+    with pytest.raises(IndexError):
+        emb.check_indices()
