@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- CTR training samples/sec of the Scenario-Wise-Rec hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one synthetic
+batch exactly as the reference trainer drives it (scenario_wise_rec/trainers/ctr_trainer.py:67-73):
+EmbeddingLayer gather -> expert / gate / tower stack -> BCELoss -> zero_grad -> backward (incl.
+embedding-gradient scatter) -> Adam(lr 1e-3, weight_decay 1e-5).
+
+* ``value``     samples/s, inputs resident in HBM, CUDA-event timed, max over ranks
+* ``e2e``       the same through ``CTRTrainer.train_step`` with pinned HOST batches: the H2D copy
+                of every feature column and a D2H read of the loss are inside the timed region
+* ``roofline``  the dominant kernel of the step, timed live with CUDA events on the launch stream
+                (swr_profile_begin/end of the C ABI), against MEASURED_PEAKS.json
+* ``cpu_baseline`` the CPU oracle port (oracle/ref_models.py + torch autograd + torch Adam) on this
+                box's host cores, bounded sample (rank 0, N=1 only)
+* ``--impl reference``: only the CPU path (the reference is pure PyTorch; its restatement
+  oracle/ref_models.py issues the same ATen ops), all host threads, same JSON keys.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "scenario-wise-rec_b200"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import workloads  # noqa: E402
+
+METRIC = "CTR training samples/sec (bs=4096 per GPU)"
+UNIT = "samples/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), bf16=float(d["bf16_tflops"]), bf16_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=3)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU path (oracle port): the reference's own algorithm on the host cores
+# --------------------------------------------------------------------------------------------
+class CpuReference:
+    """fwd + BCELoss + zero_grad + backward + Adam of the restated reference forward (oracle/ref_models.py),
+    torch CPU with every host thread.  Used for ``cpu_baseline`` and ``--impl reference`` only."""
+
+    def __init__(self, case, seed=0):
+        from oracle import ref_models
+        import model_factory
+        self.rm = ref_models
+        self.model_name, self.cfg, self.B = workloads.CASES[case]
+        torch.manual_seed(seed)
+        # parameter shapes / init come from the product's parameter containers (plain torch modules on CPU);
+        # no product compute is involved: the forward below is the oracle's.
+        m = model_factory.build(self.model_name, self.cfg)
+        self.state = {}
+        for k, v in m.state_dict().items():
+            v = v.detach().clone()
+            if v.dtype.is_floating_point and "running_" not in k:
+                v.requires_grad_(True)
+            self.state[k] = v
+        self.params = [v for v in self.state.values() if v.requires_grad]
+        self.opt = torch.optim.Adam(self.params, lr=1e-3, weight_decay=1e-5)
+        self.cores = torch.get_num_threads()
+
+    def step(self, x, y):
+        bn_out = {}
+        out = self.rm.forward(self.model_name, x, self.state, self.cfg, training=True, bn_out=bn_out)
+        loss = torch.nn.functional.binary_cross_entropy(out, y)
+        for p in self.params:
+            p.grad = None
+        loss.backward()
+        self.opt.step()
+        with torch.no_grad():
+            for k, v in bn_out.items():
+                self.state[k] = v
+        return float(loss.detach())
+
+    def time(self, steps, warmup, budget_s=None):
+        feats = workloads.all_feature_specs(self.cfg)
+        batches = [workloads.make_batch(feats, self.B, self.cfg["domain_num"], seed=100 + i) for i in range(4)]
+        for i in range(warmup):
+            self.step(*batches[i % 4])
+        t0 = time.perf_counter()
+        n = 0
+        for i in range(steps):
+            self.step(*batches[i % 4])
+            n += 1
+            if budget_s is not None and time.perf_counter() - t0 > budget_s:
+                break
+        dt = time.perf_counter() - t0
+        return n, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = CpuReference(args.workload)
+    n, dt = ref.time(args.steps, args.warmup)
+    val = n * ref.B / dt
+    sample = f"{n} full train steps of {args.workload} (B={ref.B}) after {args.warmup} warm-up"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": n, "warmup": args.warmup,
+        "ms_per_step": dt / n * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": args.workload, "device": "cpu", "path": "oracle/ref_models.py (torch CPU, same ATen ops as the reference)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": ref.cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# op costs (algorithmic bytes / flops) from the program records
+# --------------------------------------------------------------------------------------------
+def op_table(prog, feats):
+    """(pass, header index) -> dict(name, bound, work) for every op of the program."""
+    from scenario_wise_rec_b200 import _native as N
+    B = prog.B
+    names = {N.OP_ZERO: "zero", N.OP_GATHER: "gather", N.OP_SCATTER: "scatter", N.OP_COLSTATS: "colstats", N.OP_FC_FWD: "fc_fwd",
+             N.OP_FC_DGRAD: "fc_dgrad", N.OP_FC_WGRAD: "fc_wgrad", N.OP_POOL_FWD: "pool_fwd", N.OP_POOL_BWD: "pool_bwd",
+             N.OP_HEAD_FWD: "head_fwd", N.OP_HEAD_BWD: "head_bwd", N.OP_BN_UPDATE: "bn_update", N.OP_BN_PGRAD: "bn_pgrad"}
+    out = {}
+    for tag, recs in (("fwd", prog.recs_fwd), ("bwd", prog.recs_bwd)):
+        i = 0
+        while i < len(recs):
+            h = recs[i]
+            kind, ns = int(h["kind"]), int(h["n_sub"])
+            subs = recs[i + 1:i + 1 + ns]
+            d = {"name": names.get(kind, str(kind)), "bound": "hbm", "work": None}
+            if kind in (N.OP_FC_FWD, N.OP_FC_DGRAD, N.OP_FC_WGRAD):
+                fl = sum(2.0 * B * int(r["i"][1]) * int(r["i"][5]) for r in subs)
+                d.update(bound="tensor", work=fl, name=f"{d['name']}[{ns}g K{int(subs[0]['i'][1])} N{int(subs[0]['i'][5])}]")
+            elif kind == N.OP_GATHER:
+                d["work"] = float(B * workloads.gather_bytes_per_sample(feats))
+            elif kind == N.OP_SCATTER:
+                d["work"] = float(B * workloads.scatter_bytes_per_sample(feats))
+            elif kind == N.OP_ZERO:
+                d["work"] = float((int(h["i"][0]) & 0xFFFFFFFF) | (int(h["i"][1]) << 32))
+            out[(kind, i)] = d
+            i += 1 + ns
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=workloads.DEFAULT_CASE, choices=sorted(workloads.CASES))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch.distributed as dist
+    import model_factory
+    from scenario_wise_rec_b200 import _native as N
+    from scenario_wise_rec_b200.trainers import CTRTrainer
+
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N.check(N.lib().swr_device_check(), "swr_device_check")
+
+    model_name, cfg, B = workloads.CASES[args.workload]
+    feats = workloads.all_feature_specs(cfg)
+    torch.manual_seed(0)                     # identical initial weights on every rank
+    model = model_factory.build(model_name, cfg)
+    trainer = CTRTrainer(model, "synthetic", optimizer_params={"lr": 1e-3, "weight_decay": 1e-5}, device=str(dev))
+    if world > 1:
+        trainer.enable_data_parallel()
+    model.train()
+
+    NB = 8                                   # distinct batches, rotated (different rows touched every step)
+    host = [workloads.make_batch(feats, B, cfg["domain_num"], seed=1000 * rank + i, pin=True) for i in range(NB)]
+    devb = [({k: v.to(dev) for k, v in x.items()}, y.to(dev)) for x, y in host]
+    h2d = sum(v.numel() * v.element_size() for v in host[0][0].values()) + host[0][1].numel() * host[0][1].element_size()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(batches, steps, read_loss):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        l0 = N.launch_count()
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(steps):
+            loss = trainer.train_step(*batches[i % NB])
+            if read_loss:
+                loss.item()
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = e0.elapsed_time(e1)
+        launches = N.launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms, wall], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1])
+        return ms, wall, launches
+
+    for i in range(args.warmup):
+        trainer.train_step(*devb[i % NB])
+        trainer.train_step(*host[i % NB])
+    with ClockSampler(local) as clk:
+        ms, wall, launches = timed(devb, args.steps, read_loss=False)
+        ms_e2e, wall_e2e, _ = timed(host, args.steps, read_loss=True)
+    model.check_indices()
+    value = world * B * args.steps / (ms * 1e-3)
+    e2e = world * B * args.steps / (max(ms_e2e, wall_e2e) * 1e-3)
+
+    # live per-op device times (CUDA events on the launch stream around every op of the program)
+    P = min(args.steps, 20)
+    N.profile_begin()
+    for i in range(P):
+        trainer.train_step(*devb[i % NB])
+    kinds, recs, opms = N.profile_end()
+    runner = model._runner(devb[0][0])
+    tab = op_table(runner.prog, feats)
+    agg = {}
+    for k, r, t in zip(kinds.tolist(), recs.tolist(), opms.tolist()):
+        agg.setdefault((k, r), []).append(t)
+    pk = peaks()
+    ops = []
+    for key, ts in agg.items():
+        d = tab.get(key, {"name": str(key), "bound": "hbm", "work": None})
+        ops.append({"op": d["name"], "ms": float(np.mean(ts)), "bound": d["bound"], "work": d["work"]})
+    ops.sort(key=lambda o: -o["ms"])
+    top = ops[0]
+    if top["bound"] == "tensor":
+        ach = top["work"] / (top["ms"] * 1e-3) / 1e12 if top["work"] else None
+        roof = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": (ach / pk["bf16_sustained"]) if ach else None, "traffic": None}
+    else:
+        ach = top["work"] / (top["ms"] * 1e-3) / 1e9 if top["work"] else None
+        roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": (ach / pk["hbm"]) if ach else None, "traffic": None}
+    roof.update(kernel=top["op"], kernel_ms=top["ms"], peak_source=pk["source"],
+                share_of_step=top["ms"] / max(sum(o["ms"] for o in ops), 1e-9))
+    gather = next((o for o in ops if o["op"] == "gather"), None)
+    scatter = next((o for o in ops if o["op"] == "scatter"), None)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "model": model_name, "batch_per_gpu": B, "global_batch": B * world,
+                   "parallelism": f"dp{world}" if world > 1 else "single",
+                   "l2": "working set per step (tables + dense grads + Adam moments, %.0f MB) exceeds the 126 MB L2; %d rotating batches"
+                         % (4 * workloads.table_bytes(feats) / 1e6, NB),
+                   "optimizer": "Adam(lr=1e-3, weight_decay=1e-5)"},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": max(ms_e2e, wall_e2e) / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "roofline": roof,
+        "ops_ms": [{"op": o["op"], "ms": round(o["ms"], 5)} for o in ops[:12]],
+        "gather": None if not gather else {"ms": gather["ms"], "GBps": gather["work"] / gather["ms"] / 1e6, "frac_hbm": gather["work"] / gather["ms"] / 1e6 / pk["hbm"]},
+        "scatter": None if not scatter else {"ms": scatter["ms"], "GBps": scatter["work"] / scatter["ms"] / 1e6, "frac_hbm": scatter["work"] / scatter["ms"] / 1e6 / pk["hbm"]},
+        "wall_ms_per_step": wall / args.steps,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        ref = CpuReference(args.workload)
+        n, dt = ref.time(10_000, 2, budget_s=args.cpu_budget)
+        line["cpu_baseline"] = {"value": n * ref.B / dt, "unit": UNIT, "cores": ref.cores, "kind": "port",
+                                "sample": f"{n} full train steps of {args.workload} (B={ref.B}) on the host, {dt:.1f} s"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -62,6 +62,15 @@ SWR_API int64_t swr_launch_count(void);
 /* 0 if the current device is sm_100-class, else SWR_ERR_NO_DEVICE */
 SWR_API int swr_device_check(void);
 
+/* Per-op device timing of swr_program_run (bench.py's live roofline measurement).
+ * swr_profile_begin(): every op of the program runs issued by the calling thread from now
+ * on is bracketed by CUDA events on the launch stream (no synchronisation is added).
+ * swr_profile_end(): synchronises, writes for each recorded op its op kind, the index of
+ * its header record inside its program and its device time in ms (up to `cap` entries),
+ * stops profiling and returns the number of ops recorded (or a negative swr_status). */
+SWR_API int swr_profile_begin(void);
+SWR_API int swr_profile_end(int32_t* kinds, int32_t* rec_index, float* ms, int32_t cap);
+
 /* ------------------------------------------------------------------------------------
  * K1: fused multi-field embedding gather (+ dense append)
  *   out[b, f*E .. f*E+E)          = tables[f][ idx[f][b] , : ]      f < n_sparse

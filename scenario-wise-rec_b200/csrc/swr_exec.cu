@@ -23,6 +23,11 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// ---- optional per-op device timing (swr_profile_begin / swr_profile_end) ---------------
+struct ProfEntry { int kind; int rec; cudaEvent_t e0, e1; };
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfEntry> g_prof;
+
 // ---- record decoding ------------------------------------------------------------------
 struct Ctx {
   void* const* slots;
@@ -234,6 +239,11 @@ SWR_API int swr_program_run(const swr_rec_t* recs, int32_t n_recs, void* const* 
     for (int k = 0; k < h.n_sub; ++k)
       if (subs[k].kind != SWR_OP_GROUP) { set_error("program: record %d is not a group", i + 1 + k); return SWR_ERR_INVALID; }
     int rc = SWR_OK;
+    ProfEntry pe{h.kind, i, nullptr, nullptr};
+    if (g_prof_on) {
+      if (cudaEventCreate(&pe.e0) != cudaSuccess || cudaEventCreate(&pe.e1) != cudaSuccess) { set_error("profile: cudaEventCreate failed"); return SWR_ERR_CUDA; }
+      cudaEventRecord(pe.e0, st);
+    }
     switch (h.kind) {
       case SWR_OP_ZERO: {
         void* p = c.slot(h.s[0]);
@@ -257,11 +267,35 @@ SWR_API int swr_program_run(const swr_rec_t* recs, int32_t n_recs, void* const* 
       case SWR_OP_BN_PGRAD: rc = run_bn(h, subs, true, c, st); break;
       default: set_error("program: unknown op kind %d at record %d", h.kind, i); return SWR_ERR_INVALID;
     }
+    if (g_prof_on) { cudaEventRecord(pe.e1, st); g_prof.push_back(pe); }
     if (!c.ok) return SWR_ERR_INVALID;
     if (rc) return rc;
     i += 1 + h.n_sub;
   }
   return SWR_OK;
+}
+
+SWR_API int swr_profile_begin(void) {
+  for (auto& e : g_prof) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
+  g_prof.clear();
+  g_prof_on = true;
+  return SWR_OK;
+}
+
+SWR_API int swr_profile_end(int32_t* kinds, int32_t* rec_index, float* ms, int32_t cap) {
+  g_prof_on = false;
+  int n = 0;
+  int rc = SWR_OK;
+  for (auto& e : g_prof) {
+    if (cudaEventSynchronize(e.e1) != cudaSuccess) { set_error("profile: cudaEventSynchronize failed"); rc = SWR_ERR_CUDA; }
+    float t = 0.f;
+    if (rc == SWR_OK && cudaEventElapsedTime(&t, e.e0, e.e1) != cudaSuccess) { set_error("profile: cudaEventElapsedTime failed"); rc = SWR_ERR_CUDA; }
+    if (n < cap) { if (kinds) kinds[n] = e.kind; if (rec_index) rec_index[n] = e.rec; if (ms) ms[n] = t; }
+    ++n;
+    cudaEventDestroy(e.e0); cudaEventDestroy(e.e1);
+  }
+  g_prof.clear();
+  return rc ? rc : n;
 }
 
 }  // extern "C"

@@ -32,6 +32,7 @@ W_NK, W_KN = 0, 1
 DT_I8, DT_I16, DT_I32, DT_I64, DT_U8, DT_F16, DT_BF16, DT_F32, DT_F64 = 0, 1, 2, 3, 4, 8, 9, 10, 11
 
 EXPORTS = ("swr_abi_version", "swr_last_error", "swr_launch_count", "swr_device_check",
+           "swr_profile_begin", "swr_profile_end",
            "swr_embedding_gather_fwd", "swr_embedding_scatter_bwd", "swr_program_run")
 
 _lib = None
@@ -58,6 +59,9 @@ def lib():
     L.swr_embedding_gather_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, vp, vp]
     L.swr_embedding_scatter_bwd.restype = ctypes.c_int
     L.swr_embedding_scatter_bwd.argtypes = [vp, i64, i64, vp, vp, vp, vp, i32, i32, vp]
+    L.swr_profile_begin.restype = ctypes.c_int
+    L.swr_profile_end.restype = ctypes.c_int
+    L.swr_profile_end.argtypes = [vp, vp, vp, i32]
     if L.swr_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libswr_b200.so ABI {L.swr_abi_version()} != expected {ABI_VERSION}; rebuild")
     _lib = L
@@ -83,6 +87,22 @@ def program_run(recs: np.ndarray, slots: np.ndarray, stream: int):
     assert slots.dtype == np.uint64 and slots.flags.c_contiguous
     st = lib().swr_program_run(recs.ctypes.data, recs.shape[0], slots.ctypes.data, slots.shape[0], stream)
     check(st, "swr_program_run")
+
+
+def profile_begin():
+    check(lib().swr_profile_begin(), "swr_profile_begin")
+
+
+def profile_end(cap: int = 65536):
+    """-> (op kinds, header record indices, device ms) of every op run since profile_begin()."""
+    kinds = np.zeros(cap, dtype=np.int32)
+    recs = np.zeros(cap, dtype=np.int32)
+    ms = np.zeros(cap, dtype=np.float32)
+    n = lib().swr_profile_end(kinds.ctypes.data, recs.ctypes.data, ms.ctypes.data, cap)
+    if n < 0:
+        check(n, "swr_profile_end")
+    n = min(n, cap)
+    return kinds[:n], recs[:n], ms[:n]
 
 
 def torch_dtype_code(dt) -> int:

@@ -44,6 +44,8 @@ class FusedModule(nn.Module):
 
     #: runner class; tests swap in oracle.ops_ref.RefRunner to check the lowering on CPU
     _runner_factory = None
+    #: optional callable(dict arena name -> flat gradient tensor) run after every backward (data parallel)
+    _grad_sync = None
 
     def __init__(self):
         super().__init__()
@@ -79,6 +81,7 @@ class FusedModule(nn.Module):
             prog = b.finish()
             factory = type(self)._runner_factory
             r = factory(prog) if factory is not None else CudaRunner(prog, self._device())
+            r.grad_sync = self._grad_sync
             self._programs[key] = r
         return r
 

@@ -559,7 +559,7 @@ class CudaRunner:
                                f"got device {device}")
         N.lib()     # raises if the extension is not built
         self.prog, self.device = prog, device
-        self.ws32 = torch.empty(max(prog.ws32, 1), dtype=torch.float32, device=device)
+        self.ws32 = torch.zeros(max(prog.ws32, 1), dtype=torch.float32, device=device)
         self.ws64 = torch.zeros(max(prog.ws64, 1), dtype=torch.float64, device=device)
         # out-of-range index flag: mapped pinned host memory, readable without a device sync
         self.oob = torch.zeros(2, dtype=torch.int32).pin_memory()
@@ -646,4 +646,6 @@ class CudaRunner:
                 v.zero_() if g is None else v.copy_(g)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         N.program_run(prog.recs_bwd, self.ptrs, stream)
+        if getattr(self, "grad_sync", None) is not None:
+            self.grad_sync(arenas)
         return [arenas[a][off:off + n].view(p.shape) for p, (a, off, n) in zip(prog.params, prog.param_arena)]

@@ -1,0 +1,155 @@
+"""CTRTrainer with the reference's constructor and methods
+(reference: scenario_wise_rec/trainers/ctr_trainer.py:10-165).
+
+``train_one_epoch`` keeps the reference loop -- batch to device, ``model(x_dict)``,
+``BCELoss``, ``zero_grad``, ``backward``, ``optimizer.step`` (ctr_trainer.py:62-77) -- and
+the evaluation methods return the same values.  The per-batch work is delegated to
+:meth:`train_step`, which callers (bench.py) may also drive directly with one
+``(x_dict, y)`` batch of host or device tensors.
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import torch
+
+from ..basic.callback import EarlyStopper
+
+
+def _progress(it, desc):
+    try:
+        import tqdm
+        return tqdm.tqdm(it, desc=desc, smoothing=0, mininterval=1.0)
+    except ImportError:          # tqdm is a reference dependency; degrade to the bare iterator
+        return it
+
+
+class CTRTrainer(object):
+    def __init__(self, model, data_set_type, optimizer_fn=torch.optim.Adam, optimizer_params=None, scheduler_fn=None,
+                 scheduler_params=None, n_epoch=10, earlystop_patience=10, device="cpu", gpus=None, model_path="./"):
+        self.model = model
+        self.data_set_type = data_set_type
+        gpus = [] if gpus is None else gpus
+        self.gpus = gpus
+        if len(gpus) > 1:
+            raise NotImplementedError("single-process nn.DataParallel is replaced by one process per GPU "
+                                      "(torch.distributed / NCCL); launch with torchrun, see INTEGRATION.md")
+        self.device = torch.device(device)
+        self.model.to(self.device)
+        if optimizer_params is None:
+            optimizer_params = {"lr": 1e-3, "weight_decay": 1e-5}
+        self.optimizer = optimizer_fn(self.model.parameters(), **optimizer_params)
+        self.scheduler = None
+        if scheduler_fn is not None:
+            self.scheduler = scheduler_fn(self.optimizer, **scheduler_params)
+        self.criterion = torch.nn.BCELoss()
+        self.n_epoch = n_epoch
+        self.early_stopper = EarlyStopper(patience=earlystop_patience)
+        self.model_path = model_path
+
+    def enable_data_parallel(self, group=None):
+        """One process per GPU (torchrun): average the gradient arenas of every backward over the
+        process group with one NCCL all-reduce per arena (replaces nn.DataParallel, ctr_trainer.py:45-47
+        of the reference; like it, BatchNorm statistics stay per replica)."""
+        import torch.distributed as dist
+
+        def sync(arenas):
+            for a in arenas.values():
+                if a.numel() > 1:
+                    dist.all_reduce(a, op=dist.ReduceOp.AVG, group=group)
+
+        self.model._grad_sync = sync
+        self.model._programs = {}
+
+    @staticmethod
+    def evaluate_fn(targets, predicts):
+        from sklearn.metrics import roc_auc_score
+        return roc_auc_score(targets, predicts)
+
+    # ---- one batch -----------------------------------------------------------------------------
+    def train_step(self, x_dict, y):
+        """ctr_trainer.py:67-73 for one batch; returns the loss tensor (device, not synchronised)."""
+        x_dict = {k: v.to(self.device, non_blocking=True) for k, v in x_dict.items()}
+        y = y.to(self.device, non_blocking=True)
+        y_pred = self.model(x_dict)
+        loss = self.criterion(y_pred, y.float())
+        self.model.zero_grad()
+        loss.backward()
+        self.optimizer.step()
+        return loss
+
+    def train_one_epoch(self, data_loader, log_interval=10):
+        self.model.train()
+        total_loss = 0
+        tk0 = _progress(data_loader, "train")
+        for i, (x_dict, y) in enumerate(tk0):
+            loss = self.train_step(x_dict, y)
+            total_loss += loss.item()
+            if (i + 1) % log_interval == 0:
+                if hasattr(tk0, "set_postfix"):
+                    tk0.set_postfix(loss=total_loss / log_interval)
+                total_loss = 0
+
+    def fit(self, train_dataloader, val_dataloader=None):
+        for epoch_i in range(self.n_epoch):
+            print("epoch:", epoch_i)
+            self.train_one_epoch(train_dataloader)
+            if self.scheduler is not None:
+                if epoch_i % self.scheduler.step_size == 0:
+                    print("Current lr : {}".format(self.optimizer.state_dict()["param_groups"][0]["lr"]))
+                self.scheduler.step()
+            if val_dataloader:
+                auc, logloss = self.evaluate(self.model, val_dataloader)
+                print(f"epoch:{epoch_i} | val auc: {auc} | val logloss: {logloss}")
+                if self.early_stopper.stop_training(auc, self.model.state_dict()):
+                    print(f"validation: best auc: {self.early_stopper.best_auc}")
+                    self.model.load_state_dict(self.early_stopper.best_weights)
+                    break
+        time_now = time.strftime("%m_%d_%H_%M", time.localtime(int(round(time.time() * 1000)) / 1000))
+        name = self.model.__class__.__name__ + "_" + self.data_set_type + "_" + time_now + ".pth"
+        torch.save(self.model.state_dict(), os.path.join(self.model_path, name))
+
+    # ---- evaluation ------------------------------------------------------------------------------
+    def _predict_batches(self, model, data_loader, desc):
+        model.eval()
+        with torch.no_grad():
+            for x_dict, y in _progress(data_loader, desc):
+                x_dict = {k: v.to(self.device, non_blocking=True) for k, v in x_dict.items()}
+                yield x_dict, y, model(x_dict)
+        if hasattr(model, "check_indices"):
+            model.check_indices()
+
+    def evaluate(self, model, data_loader, mode="val"):
+        from sklearn.metrics import log_loss
+        targets, predicts = [], []
+        for _x, y, y_pred in self._predict_batches(model, data_loader, "validation"):
+            targets.extend(y.tolist())
+            predicts.extend(y_pred.tolist())
+        return self.evaluate_fn(targets, predicts), log_loss(targets, predicts)
+
+    def evaluate_multi_domain_loss(self, model, data_loader, domain_num):
+        from sklearn.metrics import log_loss
+        t_all, p_all = [], []
+        t_dom = [[] for _ in range(domain_num)]
+        p_dom = [[] for _ in range(domain_num)]
+        for x_dict, y, y_pred in self._predict_batches(model, data_loader, "validation"):
+            dom = x_dict["domain_indicator"].cpu()
+            y, y_pred = y.cpu(), y_pred.cpu()
+            t_all.extend(y.tolist())
+            p_all.extend(y_pred.tolist())
+            for d in range(domain_num):
+                m = dom == d
+                t_dom[d].extend(y[m].tolist())
+                p_dom[d].extend(y_pred[m].tolist())
+        logloss_d = [log_loss(t_dom[d], p_dom[d]) if t_dom[d] else None for d in range(domain_num)]
+        auc_d = [self.evaluate_fn(t_dom[d], p_dom[d]) if t_dom[d] else None for d in range(domain_num)]
+        total_logloss = log_loss(t_all, p_all) if p_all else None
+        total_auc = self.evaluate_fn(t_all, p_all) if p_all else None
+        return logloss_d, auc_d, total_logloss, total_auc
+
+    def predict(self, model, data_loader):
+        predicts = []
+        for _x, _y, y_pred in self._predict_batches(model, data_loader, "predict"):
+            predicts.extend(y_pred.tolist())
+        return predicts

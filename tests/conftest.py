@@ -7,7 +7,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG_ROOT = os.path.join(ROOT, "scenario-wise-rec_b200")
-for p in (ROOT, PKG_ROOT, os.path.join(ROOT, "tests")):
+for p in (ROOT, PKG_ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
     if p not in sys.path:
         sys.path.insert(0, p)
 

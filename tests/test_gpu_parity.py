@@ -89,33 +89,9 @@ def _prog(model, x):
 # --------------------------------------------------------------------------------------------
 # BASELINE.json shapes against the oracle run live on the host cores
 # --------------------------------------------------------------------------------------------
-ALI_VOCAB = [238635, 98, 14, 3, 8, 4, 4, 3, 5, 467298, 6929, 263942, 80232, 106399, 5888, 104830, 51878, 37148,
-             3, 5853, 105622, 53843, 31858]
+import workloads
 
-
-def ali_ccp_features(scale=1):
-    f = [(f"D{i}", "dense", 0, 1) for i in range(8)]
-    f += [(f"s{i}", "sparse", max(2, v // scale), 16) for i, v in enumerate(ALI_VOCAB)]
-    return f
-
-
-def kuairand_features():
-    vocab = [4_000_000 // 8, 1000] + [50 + 45 * i for i in range(30)]
-    return [(f"s{i}", "sparse", v, 16) for i, v in enumerate(vocab)] + [(f"D{i}", "dense", 0, 1) for i in range(4)]
-
-
-def ml1m_features():
-    return [("user_id", "sparse", 6041, 16), ("movie_id", "sparse", 3953, 16), ("gender", "sparse", 3, 16),
-            ("age", "sparse", 8, 16), ("occupation", "sparse", 22, 16), ("zip", "sparse", 3440, 16), ("d0", "dense", 0, 1)]
-
-
-BASELINE_CASES = {
-    "cfg1_sharedbottom_ml1m_b256": ("SharedBottom", dict(features=ml1m_features(), domain_num=3, bottom_dims=[128], tower_dims=[8]), 256),
-    "cfg2_mmoe_aliccp_b4096": ("MMOE", dict(features=ali_ccp_features(), domain_num=3, n_expert=4,
-                                            expert_dims=[256, 128, 64, 32, 16, 8], tower_dims=[16]), 4096),
-    "cfg3_ple_kuairand_b8192": ("PLE", dict(features=kuairand_features(), domain_num=5, n_level=1, n_expert_specific=2,
-                                            n_expert_shared=2, expert_dims=[64, 32], tower_dims=[16]), 8192),
-}
+BASELINE_CASES = {k: v for k, v in workloads.CASES.items() if k.startswith(("cfg1", "cfg2", "cfg3"))}
 
 
 @pytest.mark.parametrize("case", sorted(BASELINE_CASES))

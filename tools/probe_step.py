@@ -1,11 +1,11 @@
 """Quick device-time probe of the cfg2 MMoE train step (development aid, not the bench)."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, "scenario-wise-rec_b200"), os.path.join(ROOT, "tests")):
+for p in (ROOT, os.path.join(ROOT, "scenario-wise-rec_b200"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
     sys.path.insert(0, p)
 import torch
 import model_factory, gpu_util
-from test_gpu_parity import BASELINE_CASES
+from workloads import CASES as BASELINE_CASES
 from oracle import ref_models
 from scenario_wise_rec_b200 import _native as N
 
