@@ -63,7 +63,7 @@ SWR_API int64_t swr_launch_count(void);
 SWR_API int swr_device_check(void);
 
 /* Per-op device timing of swr_program_run (bench.py's live roofline measurement).
- * swr_profile_begin(): every op of the program runs issued by the calling thread from now
+ * swr_profile_begin(): every op of the program runs issued by this process (any thread) from now
  * on is bracketed by CUDA events on the launch stream (no synchronisation is added).
  * swr_profile_end(): synchronises, writes for each recorded op its op kind, the index of
  * its header record inside its program and its device time in ms (up to `cap` entries),
@@ -136,6 +136,18 @@ typedef enum swr_op_kind {
   SWR_OP_HEAD_BWD = 11,
   SWR_OP_BN_UPDATE = 12,  /* BatchNorm running-stat update for a list of layers        */
   SWR_OP_BN_PGRAD = 13,   /* d gamma / d beta from the reduced backward statistics     */
+  SWR_OP_EW_FWD = 14,     /* out = value(A) * value(C) * scale | value(A) + value(C) | value(A) */
+  SWR_OP_EW_BWD = 15,
+  SWR_OP_SUMGRAD = 16,    /* dst.dz (+)= sum_i dY(view_i): backward of normalised views of one
+                             raw tensor (STAR partitioned norm, star.py:95-100)          */
+  SWR_OP_SELECT_FWD = 17, /* out[b,:] = value(Y_{domain[b]})[b,:]  (M3oE star layer)     */
+  SWR_OP_SELECT_BWD = 18,
+  SWR_OP_LN_FWD = 19,     /* out = act(LayerNorm(Y)) row-wise (m3oe.py:45-68)            */
+  SWR_OP_LN_BWD = 20,
+  SWR_OP_MIX_FWD = 21,    /* M3oE domain-expert mixing with sigmoid scalar weights       */
+  SWR_OP_MIX_BWD = 22,
+  SWR_OP_BMV_FWD = 23,    /* HAMUR per-sample q[b,:] = p[b,:] * H_b (hamur.py:177-189)   */
+  SWR_OP_BMV_BWD = 24,
   SWR_OP_GROUP = 100      /* a group record belonging to the preceding header          */
 } swr_op_kind;
 
@@ -145,6 +157,10 @@ enum { SWR_NORM_NONE = 0, SWR_NORM_BATCH = 1, SWR_NORM_RUNNING = 2 };
 enum { SWR_ACT_NONE = 0, SWR_ACT_RELU = 1, SWR_ACT_SIGMOID = 2, SWR_ACT_LEAKY = 3 };
 /* weight layouts */
 enum { SWR_W_NK = 0 /* nn.Linear [N,K] */, SWR_W_KN = 1 /* STAR [K,N] */ };
+/* element-wise modes of SWR_OP_EW_* */
+enum { SWR_EW_MUL = 0, SWR_EW_ADD = 1, SWR_EW_COPY = 2 };
+/* head modes: select(sigmoid(v_d)) | sigmoid(select(v_d) + add) | sigmoid(v_0) for every row */
+enum { SWR_HEAD_SELECT_SIG = 1, SWR_HEAD_SIG_SELECT_ADD = 0, SWR_HEAD_NO_SELECT = 2 };
 
 SWR_API int swr_program_run(const swr_rec_t* recs, int32_t n_recs, void* const* slots,
                     int32_t n_slots, void* stream);

@@ -20,7 +20,10 @@ import torch
 OP_ZERO, OP_GATHER, OP_SCATTER, OP_COLSTATS = 1, 2, 3, 4
 OP_FC_FWD, OP_FC_DGRAD, OP_FC_WGRAD = 5, 6, 7
 OP_POOL_FWD, OP_POOL_BWD, OP_HEAD_FWD, OP_HEAD_BWD = 8, 9, 10, 11
-OP_BN_UPDATE, OP_BN_PGRAD, OP_NORM_BWD, OP_GROUP = 12, 13, 14, 100
+OP_BN_UPDATE, OP_BN_PGRAD, OP_GROUP = 12, 13, 100
+OP_EW_FWD, OP_EW_BWD, OP_SUMGRAD, OP_SELECT_FWD, OP_SELECT_BWD = 14, 15, 16, 17, 18
+OP_LN_FWD, OP_LN_BWD, OP_MIX_FWD, OP_MIX_BWD, OP_BMV_FWD, OP_BMV_BWD = 19, 20, 21, 22, 23, 24
+EW_MUL, EW_ADD, EW_COPY = 0, 1, 2
 NORM_NONE, NORM_BATCH, NORM_RUNNING = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_LEAKY = 0, 1, 2, 3
 
@@ -53,8 +56,10 @@ class _Act:
         s, i, f = rec["s"], rec["i"], rec["f"]
         self.ld, self.n, self.mode, self.act = int(i[ib]), int(i[ib + 1]), int(i[ib + 2]), int(i[ib + 3])
         self.eps = float(f[fb])
+        self.var_scale = float(f[fb + 1])
         B = run.prog.B
-        v2 = lambda slot: None if slot < 0 else run.slot(slot)[:B * self.ld].view(B, self.ld)[:, :self.n]   # noqa: E731
+        # strided view: a column sub-view starts inside a row, so its last row is shorter than ld
+        v2 = lambda slot: None if slot < 0 else torch.as_strided(run.slot(slot), (B, self.n), (self.ld, 1))   # noqa: E731
         v1 = lambda slot: None if slot < 0 else run.slot(slot).reshape(-1)[:self.n]                           # noqa: E731
         self.raw = v2(int(s[sb]))
         self.stats = None if s[sb + 1] < 0 else run.slot(int(s[sb + 1]))[:2 * self.n].view(self.n, 2)
@@ -73,7 +78,7 @@ class _Act:
             return z, torch.ones(n), z.clone(), torch.ones(n)
         if self.mode == NORM_BATCH:
             mu = self.stats[:, 0] / self.B
-            var = (self.stats[:, 1] / self.B - mu * mu).clamp_min(0.0)
+            var = (self.stats[:, 1] / self.B - mu * mu).clamp_min(0.0) * self.var_scale
         else:
             mu, var = self.rmean.double(), self.rvar.double()
         r = (1.0 / torch.sqrt(var + self.eps)).float()
@@ -122,8 +127,9 @@ class _Act:
             return self.dz * s
         S1, S2 = self.dstats[:, 0], self.dstats[:, 1]
         sd, rd, mud, ib = s.double(), r.double(), mu.double(), 1.0 / self.B
-        c1 = (-sd * rd * S2 * ib).float()
-        c2 = (-sd * S1 * ib + sd * rd * S2 * mud * ib).float()
+        ibv = ib * self.var_scale
+        c1 = (-sd * rd * S2 * ibv).float()
+        c2 = (-sd * S1 * ib + sd * rd * S2 * mud * ibv).float()
         return s * self.dz + c1 * self.raw + c2
 
 
@@ -217,7 +223,7 @@ class RefRunner:
 
     def _op_2(self, h, subs):       # GATHER
         B, ld = int(h["i"][0]), int(h["i"][4])
-        out = self.slot(int(h["s"][0]))[:B * ld].view(B, ld)
+        out = self.slot(int(h["s"][0]))[:B * ld].view(B, ld)      # sub-records carry absolute columns
         for f, r in enumerate(subs):
             col = int(r["i"][3])
             if int(r["i"][4]) == 0:
@@ -283,7 +289,7 @@ class RefRunner:
             t = Y.dy() @ self._weff(r)
             dA = t if dA is None else dA + t
         D = _Act(self, subs[0], 0, 0, 0)
-        D.write_grad(dA, accumulate=bool(int(subs[0]["i"][11]) & 2))
+        D.write_grad(dA[:, :D.n], accumulate=bool(int(subs[0]["i"][11]) & 2))    # D.n < K: detached trailing columns
 
     def _op_7(self, h, subs):       # FC_WGRAD
         for r in subs:
@@ -345,9 +351,12 @@ class RefRunner:
     # -- head -----------------------------------------------------------------------------------
     def _op_10(self, h, subs):      # HEAD_FWD
         B = self.prog.B
-        dom = self.slot(int(h["s"][0])).long()
+        dom = self.slot(int(h["s"][0])).long() if h["s"][0] >= 0 else None
         out = self.slot(int(h["s"][1]))[:B]
-        sbs = int(h["i"][2]) == 1
+        mode = int(h["i"][2])
+        sbs = mode != 0
+        if mode == 2:
+            dom = torch.zeros(B, dtype=torch.long)
         v = torch.zeros(B)
         sel_any = torch.zeros(B, dtype=torch.bool)
         for d, r in enumerate(subs):
@@ -365,18 +374,21 @@ class RefRunner:
         if sbs:
             out.copy_(torch.where(sel_any, torch.sigmoid(v), torch.zeros(B)))
         else:
-            add = self.slot(int(h["s"][3]))[:B] if h["s"][3] >= 0 else 0.0
+            add = self._plain(h["s"][3], max(int(h["i"][4]), 1), 1)[:, 0] if h["s"][3] >= 0 else 0.0
             out.copy_(torch.sigmoid(v + add))
 
     def _op_11(self, h, subs):      # HEAD_BWD
         B = self.prog.B
-        dom = self.slot(int(h["s"][0])).long()
+        dom = self.slot(int(h["s"][0])).long() if h["s"][0] >= 0 else None
         y = self.slot(int(h["s"][1]))[:B]
         g = self.slot(int(h["s"][2]))[:B]
-        sbs = int(h["i"][2]) == 1
+        mode = int(h["i"][2])
+        sbs = mode != 0
+        if mode == 2:
+            dom = torch.zeros(B, dtype=torch.long)
         dsig = g * y * (1 - y)
         if not sbs and h["s"][4] >= 0:
-            self.slot(int(h["s"][4]))[:B].copy_(dsig)
+            self._plain(h["s"][4], max(int(h["i"][4]), 1), 1)[:, 0].copy_(dsig)
         for d, r in enumerate(subs):
             A = _Act(self, r, 0, 0, 0)
             dv = torch.where(dom == d, dsig, torch.zeros(B))
@@ -398,10 +410,12 @@ class RefRunner:
             A = _Act(self, r, 0, 0, 0)
             mu = A.stats[:, 0] / B
             var = (A.stats[:, 1] / B - mu * mu).clamp_min(0.0) * (B / (B - 1) if B > 1 else 1.0)
-            A.rmean.copy_((1 - m) * A.rmean + m * mu.float())
-            A.rvar.copy_((1 - m) * A.rvar + m * var.float())
+            rep = max(int(r["i"][8]), 1)
+            for _ in range(rep):
+                A.rmean.copy_((1 - m) * A.rmean + m * mu.float())
+                A.rvar.copy_((1 - m) * A.rvar + m * var.float())
             if r["s"][24] >= 0:
-                self.slot(int(r["s"][24])).add_(1)
+                self.slot(int(r["s"][24])).add_(rep)
 
     def _op_13(self, h, subs):      # BN_PGRAD
         for r in subs:
@@ -418,3 +432,152 @@ class RefRunner:
                 self.slot(int(s[26])).add_(s1)
             if s[27] >= 0:
                 self.slot(int(s[27])).add_(s1)
+
+    # -- element-wise glue -----------------------------------------------------------------------------
+    def _plain(self, slot, ld, n):
+        return None if slot < 0 else torch.as_strided(self.slot(int(slot)), (self.prog.B, n), (ld, 1))
+
+    def _ew_decode(self, r):
+        mode = int(r["i"][9])
+        A = _Act(self, r, 0, 0, 0)
+        C = _Act(self, r, 12, 4, 2) if mode != EW_COPY else None
+        ld = int(r["i"][8])
+        return mode, A, C, self._plain(r["s"][24], ld, A.n), self._plain(r["s"][25], ld, A.n), float(r["f"][4]), int(r["i"][10])
+
+    def _op_14(self, h, subs):      # EW_FWD
+        for r in subs:
+            mode, A, C, out, _dout, scale, _fl = self._ew_decode(r)
+            if mode == EW_MUL:
+                out.copy_(A.value() * C.value() * scale)
+            elif mode == EW_ADD:
+                out.copy_(A.value() + C.value())
+            else:
+                out.copy_(A.value())
+
+    def _op_15(self, h, subs):      # EW_BWD
+        for r in subs:
+            mode, A, C, _out, dout, scale, fl = self._ew_decode(r)
+            if mode == EW_MUL:
+                dA, dC = dout * C.value() * scale, dout * A.value() * scale
+            else:
+                dA, dC = dout, dout
+            if fl & 1:
+                A.write_grad(dA, accumulate=bool(fl & 4))
+            if C is not None and fl & 2:
+                C.write_grad(dC, accumulate=bool(fl & 8))
+
+    def _op_16(self, h, subs):      # SUMGRAD
+        dst = _Act(self, subs[0], 0, 0, 0)
+        total = sum(_Act(self, r, 0, 0, 0).dy() for r in subs[1:])
+        if int(h["i"][1]):
+            dst.dz += total
+        else:
+            dst.dz.copy_(total)
+
+    def _select_decode(self, h, subs):
+        n, ld = int(h["i"][1]), int(h["i"][2])
+        dom = self.slot(int(h["s"][0])).long()
+        return [_Act(self, r, 0, 0, 0) for r in subs], dom, self._plain(h["s"][1], ld, n), self._plain(h["s"][2], ld, n)
+
+    def _op_17(self, h, subs):      # SELECT_FWD
+        ys, dom, out, _ = self._select_decode(h, subs)
+        out.zero_()
+        for d, y in enumerate(ys):
+            out.copy_(torch.where((dom == d).unsqueeze(1), y.value(), out))
+
+    def _op_18(self, h, subs):      # SELECT_BWD
+        ys, dom, _out, dout = self._select_decode(h, subs)
+        for d, y in enumerate(ys):
+            y.write_grad(torch.where((dom == d).unsqueeze(1), dout, torch.zeros_like(dout)))
+
+    def _ln_decode(self, r):
+        s, i = r["s"], r["i"]
+        ld_y, n, ld_o, act = int(i[0]), int(i[1]), int(i[2]), int(i[3])
+        vec = lambda k: None if s[k] < 0 else self.slot(int(s[k])).reshape(-1)[:n]      # noqa: E731
+        rs = self.slot(int(s[8]))[:2 * self.prog.B].view(self.prog.B, 2)
+        return (self._plain(s[0], ld_y, n), self._plain(s[1], ld_y, n), vec(2), vec(3), vec(4), vec(5),
+                self._plain(s[6], ld_o, n), self._plain(s[7], ld_o, n), rs, act, float(r["f"][0]))
+
+    def _op_19(self, h, subs):      # LN_FWD
+        for r in subs:
+            y, _dy, gamma, beta, _dg, _db, out, _dout, rs, act, eps = self._ln_decode(r)
+            mean = y.mean(dim=1)
+            rstd = 1.0 / torch.sqrt(((y - mean.unsqueeze(1)) ** 2).mean(dim=1) + eps)
+            rs[:, 0], rs[:, 1] = mean, rstd
+            out.copy_(act_fwd((y - mean.unsqueeze(1)) * rstd.unsqueeze(1) * gamma + beta, act))
+
+    def _op_20(self, h, subs):      # LN_BWD
+        for r in subs:
+            y, dy, gamma, beta, dgam, dbet, _out, dout, rs, act, _eps = self._ln_decode(r)
+            xh = (y - rs[:, 0:1]) * rs[:, 1:2]
+            dz = dout * act_grad(xh * gamma + beta, act)
+            if dgam is not None:
+                dgam.add_((dz * xh).sum(0))
+            if dbet is not None:
+                dbet.add_(dz.sum(0))
+            g = dz * gamma
+            if dy is not None:
+                dy.copy_(rs[:, 1:2] * (g - g.mean(dim=1, keepdim=True) - xh * (g * xh).mean(dim=1, keepdim=True)))
+
+    def _mix_decode(self, h, subs):
+        D, H, ldx, ldo = int(h["i"][1]), int(h["i"][2]), int(h["i"][3]), int(h["i"][4])
+        X = [self._plain(r["s"][0], ldx, H) for r in subs]
+        dX = [self._plain(r["s"][1], ldx, H) for r in subs]
+        O = [self._plain(r["s"][2], ldo, H) for r in subs]
+        dO = [self._plain(r["s"][3], ldo, H) for r in subs]
+        se = torch.sigmoid(self.slot(int(h["s"][0])).reshape(-1)[0])
+        sb = torch.sigmoid(self.slot(int(h["s"][1])).reshape(-1)[0])
+        cc = (1 - sb) / (D - 1) if D > 1 else torch.zeros(())
+        return D, X, dX, O, dO, se, sb, cc
+
+    def _op_21(self, h, subs):      # MIX_FWD
+        D, X, _dX, O, _dO, se, sb, cc = self._mix_decode(h, subs)
+        tot = sum(X)
+        for d in range(D):
+            O[d] += se * (sb * X[d] + cc * (tot - X[d]))
+
+    def _op_22(self, h, subs):      # MIX_BWD
+        D, X, dX, O, dO, se, sb, cc = self._mix_decode(h, subs)
+        sx, sg = sum(X), sum(dO)
+        p1 = sum((dO[d].double() * X[d].double()).sum() for d in range(D))
+        p2 = sum((dO[d].double() * (sx - X[d]).double()).sum() for d in range(D))
+        for d in range(D):
+            if dX[d] is not None:
+                dX[d].copy_(se * (sb * dO[d] + cc * (sg - dO[d])))
+        dse = sb.double() * p1 + cc.double() * p2
+        dsb = se.double() * (p1 - (p2 / (D - 1) if D > 1 else 0.0))
+        if h["s"][2] >= 0:
+            self.slot(int(h["s"][2])).reshape(-1)[0] += float(dse * se * (1 - se))
+        if h["s"][3] >= 0:
+            self.slot(int(h["s"][3])).reshape(-1)[0] += float(dsb * sb * (1 - sb))
+
+    def _bmv_decode(self, h, subs):
+        k, ldh = int(h["i"][1]), int(h["i"][2])
+        B = self.prog.B
+        H = self._plain(h["s"][0], ldh, k * k).reshape(B, k, k)
+        dH = self._plain(h["s"][1], ldh, k * k)
+        gs = []
+        for r in subs:
+            ldp, ldq = int(r["i"][0]), int(r["i"][1])
+            gs.append((self._plain(r["s"][0], ldp, k), self._plain(r["s"][1], ldp, k),
+                       self._plain(r["s"][2], ldq, k), self._plain(r["s"][3], ldq, k)))
+        return k, H, dH, gs
+
+    def _op_23(self, h, subs):      # BMV_FWD
+        _k, H, _dH, gs = self._bmv_decode(h, subs)
+        for p_, _dp, q, _dq in gs:
+            q.copy_(torch.einsum("bi,bij->bj", p_, H))
+
+    def _op_24(self, h, subs):      # BMV_BWD
+        k, H, dH, gs = self._bmv_decode(h, subs)
+        tot = None
+        for p_, dp, _q, dq in gs:
+            if dp is not None:
+                dp.copy_(torch.einsum("bj,bij->bi", dq, H))
+            t = torch.einsum("bi,bj->bij", p_, dq).reshape(self.prog.B, k * k)
+            tot = t if tot is None else tot + t
+        if dH is not None:
+            if int(h["i"][3]):
+                dH += tot
+            else:
+                dH.copy_(tot)

@@ -28,7 +28,8 @@ struct NormRef {
   const float* beta2;
   int mode;
   float eps;
-  float var_scale;       // reserved (unbiased-variance norms); 1 for BatchNorm
+  float var_scale;       // variance used = var_scale * biased batch variance: 1 for BatchNorm / STAR,
+                         // B/(B-1) for HAMUR's domain norm (tmp_out.var(dim=0), hamur.py:192-195)
 };
 
 struct ActDev {
@@ -58,6 +59,7 @@ __device__ __forceinline__ void col_moments(const NormRef& nr, int c, float inv_
     mu = s1 * (double)inv_count;
     var = s2 * (double)inv_count - mu * mu;
     if (var < 0.0) var = 0.0;
+    var *= (double)nr.var_scale;
   } else {
     mu = (double)__ldg(nr.rmean + c);
     var = (double)__ldg(nr.rvar + c);
@@ -77,7 +79,7 @@ __device__ __forceinline__ ColCoef col_coef(const NormRef& nr, int c, float inv_
 }
 
 // Stage 2 of the BatchNorm backward for the column c of activation `a`:
-//   batch  : dY = s * (dz - S1/B - xhat * S2/B)     S1 = sum dz, S2 = sum dz*xhat
+//   batch  : dY = s * (dz - S1/B - v * xhat * S2/B)  S1 = sum dz, S2 = sum dz*xhat, v = var_scale
 //   running: dY = s * dz
 //   none   : dY = dz
 __device__ __forceinline__ DyCoef dy_coef(const ActDev& a, int c, float inv_count) {
@@ -87,9 +89,10 @@ __device__ __forceinline__ DyCoef dy_coef(const ActDev& a, int c, float inv_coun
   d.c0 = k.s;
   if (a.norm.mode == SWR_NORM_RUNNING) { d.c1 = 0.f; d.c2 = 0.f; return d; }
   const double S1 = __ldcg(a.dstats + 2 * c), S2 = __ldcg(a.dstats + 2 * c + 1);
-  const double s = (double)k.s, r = (double)k.r, mu = (double)k.mu, ib = (double)inv_count;
+  const double s = (double)k.s, r = (double)k.r, mu = (double)k.mu, ib = (double)inv_count * (double)a.norm.var_scale;
+  const double ib1 = (double)inv_count;
   d.c1 = (float)(-s * r * S2 * ib);
-  d.c2 = (float)(-s * S1 * ib + s * r * S2 * mu * ib);
+  d.c2 = (float)(-s * S1 * ib1 + s * r * S2 * mu * ib);
   return d;
 }
 

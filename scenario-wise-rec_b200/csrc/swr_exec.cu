@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "swr_common.cuh"
@@ -25,8 +26,10 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ---- optional per-op device timing (swr_profile_begin / swr_profile_end) ---------------
 struct ProfEntry { int kind; int rec; cudaEvent_t e0, e1; };
-static thread_local bool g_prof_on = false;
-static thread_local std::vector<ProfEntry> g_prof;
+// process-wide: autograd runs the backward program on its own thread
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;
+static std::vector<ProfEntry> g_prof;
 
 // ---- record decoding ------------------------------------------------------------------
 struct Ctx {
@@ -111,7 +114,7 @@ static int run_gather(const swr_rec_t& h, const swr_rec_t* subs, Ctx& c, cudaStr
   }
   if (!c.ok) return SWR_ERR_INVALID;
   GatherLaunch g{tables.data(), vocab.data(), idx.data(), idt.data(), E.data(), dense.data(), ddt.data(),
-                 static_cast<float*>(c.slot(h.s[0])), h.i[4], h.i[0], (int)tables.size(), (int)dense.size(),
+                 static_cast<float*>(c.slot(h.s[0])) + h.i[5], h.i[4], h.i[0], (int)tables.size(), (int)dense.size(),
                  static_cast<int32_t*>(c.slot(h.s[1]))};
   return launch_gather(g, st);
 }
@@ -162,7 +165,7 @@ static int run_head(const swr_rec_t& h, const swr_rec_t* subs, bool bwd, Ctx& c,
   }
   HeadLaunch l{dom.data(), nd, c.slot(h.s[0]), h.i[3], static_cast<float*>(c.slot(h.s[1])),
                static_cast<const float*>(c.slot(h.s[2])), static_cast<const float*>(c.slot(h.s[3])),
-               static_cast<float*>(c.slot(h.s[4])), h.i[2], h.i[0]};
+               static_cast<float*>(c.slot(h.s[4])), h.i[4] > 0 ? h.i[4] : 1, h.i[2], h.i[0]};
   if (!c.ok) return SWR_ERR_INVALID;
   return bwd ? launch_head_bwd(l, st) : launch_head_fwd(l, st);
 }
@@ -179,10 +182,94 @@ static int run_bn(const swr_rec_t& h, const swr_rec_t* subs, bool pgrad, Ctx& c,
     } else {
       layers[i].rmean = const_cast<float*>(layers[i].A.norm.rmean); layers[i].rvar = const_cast<float*>(layers[i].A.norm.rvar);
       layers[i].nbt = static_cast<int64_t*>(c.slot(r.s[24]));
+      layers[i].repeat = r.i[8];
     }
   }
   if (!c.ok) return SWR_ERR_INVALID;
   return pgrad ? launch_bn_pgrad(layers.data(), n, h.i[0], st) : launch_bn_update(layers.data(), n, h.i[0], h.f[4], st);
+}
+
+// ---- glue ops ---------------------------------------------------------------------------
+static int run_ew(const swr_rec_t* subs, int n, int64_t B, bool bwd, Ctx& c, cudaStream_t st) {
+  std::vector<EwGroup> g(n);
+  for (int i = 0; i < n; ++i) {
+    const swr_rec_t& r = subs[i];
+    g[i].A = decode_act(r, 0, 0, 0, c);
+    g[i].mode = r.i[9];
+    if (g[i].mode != SWR_EW_COPY) g[i].C = decode_act(r, 12, 4, 2, c);
+    g[i].out = static_cast<float*>(c.slot(r.s[24])); g[i].dout = static_cast<const float*>(c.slot(r.s[25]));
+    g[i].ld_out = r.i[8]; g[i].flags = r.i[10]; g[i].scale = r.f[4];
+  }
+  if (!c.ok) return SWR_ERR_INVALID;
+  return bwd ? launch_ew_bwd(g.data(), n, B, st) : launch_ew_fwd(g.data(), n, B, st);
+}
+
+static int run_sumgrad(const swr_rec_t& h, const swr_rec_t* subs, Ctx& c, cudaStream_t st) {
+  if (h.n_sub < 2 || h.n_sub - 1 > kMaxViews) { set_error("sumgrad: %d views unsupported", h.n_sub - 1); return SWR_ERR_UNSUPPORTED; }
+  SumGradLaunch l{};
+  l.dst = decode_act(subs[0], 0, 0, 0, c);
+  l.n_views = h.n_sub - 1; l.accumulate = h.i[1]; l.B = h.i[0];
+  for (int v = 0; v < l.n_views; ++v) l.views[v] = decode_act(subs[1 + v], 0, 0, 0, c);
+  if (!c.ok) return SWR_ERR_INVALID;
+  return launch_sumgrad(l, st);
+}
+
+static int run_select(const swr_rec_t& h, const swr_rec_t* subs, bool bwd, Ctx& c, cudaStream_t st) {
+  if (h.n_sub <= 0 || h.n_sub > 16) { set_error("select: %d domains unsupported", h.n_sub); return SWR_ERR_UNSUPPORTED; }
+  SelectLaunch l{};
+  l.n_domains = h.n_sub;
+  for (int d = 0; d < h.n_sub; ++d) l.Y[d] = decode_act(subs[d], 0, 0, 0, c);
+  l.domain_id = c.slot(h.s[0]); l.dom_dtype = h.i[3];
+  l.out = static_cast<float*>(c.slot(h.s[1])); l.dout = static_cast<const float*>(c.slot(h.s[2]));
+  l.n = h.i[1]; l.ld_out = h.i[2]; l.B = h.i[0];
+  if (!c.ok) return SWR_ERR_INVALID;
+  return bwd ? launch_select_bwd(l, st) : launch_select_fwd(l, st);
+}
+
+static int run_ln(const swr_rec_t* subs, int n, int64_t B, bool bwd, Ctx& c, cudaStream_t st) {
+  std::vector<LnGroup> g(n);
+  for (int i = 0; i < n; ++i) {
+    const swr_rec_t& r = subs[i];
+    g[i].y = static_cast<const float*>(c.slot(r.s[0])); g[i].dy = static_cast<float*>(c.slot(r.s[1]));
+    g[i].gamma = static_cast<const float*>(c.slot(r.s[2])); g[i].beta = static_cast<const float*>(c.slot(r.s[3]));
+    g[i].dgamma = static_cast<float*>(c.slot(r.s[4])); g[i].dbeta = static_cast<float*>(c.slot(r.s[5]));
+    g[i].out = static_cast<float*>(c.slot(r.s[6])); g[i].dout = static_cast<const float*>(c.slot(r.s[7]));
+    g[i].rowstats = static_cast<float*>(c.slot(r.s[8]));
+    g[i].ld_y = r.i[0]; g[i].n = r.i[1]; g[i].ld_out = r.i[2]; g[i].act = r.i[3]; g[i].eps = r.f[0];
+  }
+  if (!c.ok) return SWR_ERR_INVALID;
+  return bwd ? launch_ln_bwd(g.data(), n, B, st) : launch_ln_fwd(g.data(), n, B, st);
+}
+
+static int run_mix(const swr_rec_t& h, const swr_rec_t* subs, bool bwd, Ctx& c, cudaStream_t st) {
+  if (h.n_sub <= 0 || h.n_sub > 16 || h.n_sub != h.i[1]) { set_error("mix: bad domain count"); return SWR_ERR_INVALID; }
+  MixLaunch m{};
+  m.w_exp = static_cast<const float*>(c.slot(h.s[0])); m.w_bal = static_cast<const float*>(c.slot(h.s[1]));
+  m.dw_exp = static_cast<float*>(c.slot(h.s[2])); m.dw_bal = static_cast<float*>(c.slot(h.s[3]));
+  m.red = static_cast<double*>(c.slot(h.s[4]));
+  m.D = h.i[1]; m.H = h.i[2]; m.ldx = h.i[3]; m.ldo = h.i[4]; m.B = h.i[0];
+  for (int d = 0; d < m.D; ++d) {
+    const swr_rec_t& r = subs[d];
+    m.X[d] = static_cast<const float*>(c.slot(r.s[0])); m.dX[d] = static_cast<float*>(c.slot(r.s[1]));
+    m.out[d] = static_cast<float*>(c.slot(r.s[2])); m.dout[d] = static_cast<const float*>(c.slot(r.s[3]));
+  }
+  if (!c.ok) return SWR_ERR_INVALID;
+  return bwd ? launch_mix_bwd(m, st) : launch_mix_fwd(m, st);
+}
+
+static int run_bmv(const swr_rec_t& h, const swr_rec_t* subs, bool bwd, Ctx& c, cudaStream_t st) {
+  if (h.n_sub <= 0 || h.n_sub > 16) { set_error("bmv: %d groups unsupported", h.n_sub); return SWR_ERR_UNSUPPORTED; }
+  BmvLaunch m{};
+  m.H = static_cast<const float*>(c.slot(h.s[0])); m.dH = static_cast<float*>(c.slot(h.s[1]));
+  m.k = h.i[1]; m.ldh = h.i[2]; m.accumulate_dH = h.i[3]; m.B = h.i[0]; m.n_groups = h.n_sub;
+  for (int g = 0; g < h.n_sub; ++g) {
+    const swr_rec_t& r = subs[g];
+    m.g[g].p = static_cast<const float*>(c.slot(r.s[0])); m.g[g].dp = static_cast<float*>(c.slot(r.s[1]));
+    m.g[g].q = static_cast<float*>(c.slot(r.s[2])); m.g[g].dq = static_cast<const float*>(c.slot(r.s[3]));
+    m.g[g].ldp = r.i[0]; m.g[g].ldq = r.i[1];
+  }
+  if (!c.ok) return SWR_ERR_INVALID;
+  return bwd ? launch_bmv_bwd(m, st) : launch_bmv_fwd(m, st);
 }
 
 }  // namespace swr
@@ -240,7 +327,8 @@ SWR_API int swr_program_run(const swr_rec_t* recs, int32_t n_recs, void* const* 
       if (subs[k].kind != SWR_OP_GROUP) { set_error("program: record %d is not a group", i + 1 + k); return SWR_ERR_INVALID; }
     int rc = SWR_OK;
     ProfEntry pe{h.kind, i, nullptr, nullptr};
-    if (g_prof_on) {
+    const bool prof = g_prof_on.load(std::memory_order_relaxed);
+    if (prof) {
       if (cudaEventCreate(&pe.e0) != cudaSuccess || cudaEventCreate(&pe.e1) != cudaSuccess) { set_error("profile: cudaEventCreate failed"); return SWR_ERR_CUDA; }
       cudaEventRecord(pe.e0, st);
     }
@@ -265,9 +353,20 @@ SWR_API int swr_program_run(const swr_rec_t* recs, int32_t n_recs, void* const* 
       case SWR_OP_HEAD_BWD: rc = run_head(h, subs, true, c, st); break;
       case SWR_OP_BN_UPDATE: rc = run_bn(h, subs, false, c, st); break;
       case SWR_OP_BN_PGRAD: rc = run_bn(h, subs, true, c, st); break;
+      case SWR_OP_EW_FWD: rc = run_ew(subs, h.n_sub, h.i[0], false, c, st); break;
+      case SWR_OP_EW_BWD: rc = run_ew(subs, h.n_sub, h.i[0], true, c, st); break;
+      case SWR_OP_SUMGRAD: rc = run_sumgrad(h, subs, c, st); break;
+      case SWR_OP_SELECT_FWD: rc = run_select(h, subs, false, c, st); break;
+      case SWR_OP_SELECT_BWD: rc = run_select(h, subs, true, c, st); break;
+      case SWR_OP_LN_FWD: rc = run_ln(subs, h.n_sub, h.i[0], false, c, st); break;
+      case SWR_OP_LN_BWD: rc = run_ln(subs, h.n_sub, h.i[0], true, c, st); break;
+      case SWR_OP_MIX_FWD: rc = run_mix(h, subs, false, c, st); break;
+      case SWR_OP_MIX_BWD: rc = run_mix(h, subs, true, c, st); break;
+      case SWR_OP_BMV_FWD: rc = run_bmv(h, subs, false, c, st); break;
+      case SWR_OP_BMV_BWD: rc = run_bmv(h, subs, true, c, st); break;
       default: set_error("program: unknown op kind %d at record %d", h.kind, i); return SWR_ERR_INVALID;
     }
-    if (g_prof_on) { cudaEventRecord(pe.e1, st); g_prof.push_back(pe); }
+    if (prof) { cudaEventRecord(pe.e1, st); std::lock_guard<std::mutex> lk(g_prof_mu); g_prof.push_back(pe); }
     if (!c.ok) return SWR_ERR_INVALID;
     if (rc) return rc;
     i += 1 + h.n_sub;
@@ -276,6 +375,7 @@ SWR_API int swr_program_run(const swr_rec_t* recs, int32_t n_recs, void* const* 
 }
 
 SWR_API int swr_profile_begin(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   for (auto& e : g_prof) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
   g_prof.clear();
   g_prof_on = true;
@@ -284,6 +384,7 @@ SWR_API int swr_profile_begin(void) {
 
 SWR_API int swr_profile_end(int32_t* kinds, int32_t* rec_index, float* ms, int32_t cap) {
   g_prof_on = false;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   int n = 0;
   int rc = SWR_OK;
   for (auto& e : g_prof) {

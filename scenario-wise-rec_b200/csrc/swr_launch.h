@@ -69,8 +69,9 @@ struct HeadLaunch {
   const HeadDomain* dom; int n_domains;
   const void* domain_id; int dom_dtype;
   float* out; const float* gout;           // [B]
-  const float* add; float* dadd;           // optional plain [B] added before the sigmoid (STAR aux)
-  int sig_before_select;                   // 1: select(sigmoid(v_d))   0: sigmoid(select(v_d) + add)
+  const float* add; float* dadd;           // optional plain [B, ld_add] column added before the sigmoid (STAR aux)
+  int ld_add;
+  int sig_before_select;                   // 1: select(sigmoid(v_d))   0: sigmoid(select(v_d) + add)   2: sigmoid(v_0), no select
   int64_t B;
 };
 int launch_head_fwd(const HeadLaunch& h, cudaStream_t st);
@@ -78,10 +79,63 @@ int launch_head_bwd(const HeadLaunch& h, cudaStream_t st);
 
 struct BnLayer {
   ActDev A;
+  int repeat;                                          // BN_UPDATE: apply the update this many times (HAMUR shared hyper-net)
   float* rmean; float* rvar; int64_t* nbt;            // BN_UPDATE
   float* dgamma; float* dgamma2; float* dbeta; float* dbeta2;   // BN_PGRAD
 };
 int launch_bn_update(const BnLayer* layers, int n, int64_t B, float momentum, cudaStream_t st);
 int launch_bn_pgrad(const BnLayer* layers, int n, int64_t B, cudaStream_t st);
+
+// ---- element-wise / row-local glue (swr_glue.cu) ------------------------------------------------
+struct EwGroup {
+  ActDev A, C;              // C unused for SWR_EW_COPY
+  float* out; const float* dout; int ld_out;   // plain [B, n] result and its gradient
+  int mode; float scale;
+  int flags;                // bit0 A needs grad, bit1 C needs grad, bit2 accumulate into A.dz, bit3 accumulate into C.dz
+};
+enum { EW_A_GRAD = 1, EW_C_GRAD = 2, EW_A_ACC = 4, EW_C_ACC = 8 };
+int launch_ew_fwd(const EwGroup* g, int n_groups, int64_t B, cudaStream_t st);
+int launch_ew_bwd(const EwGroup* g, int n_groups, int64_t B, cudaStream_t st);
+
+constexpr int kMaxViews = 16;
+struct SumGradLaunch { ActDev dst; ActDev views[kMaxViews]; int n_views; int accumulate; int64_t B; };
+int launch_sumgrad(const SumGradLaunch& s, cudaStream_t st);
+
+struct SelectLaunch {
+  ActDev Y[16]; int n_domains;
+  const void* domain_id; int dom_dtype;
+  float* out; const float* dout; int ld_out; int n; int64_t B;
+};
+int launch_select_fwd(const SelectLaunch& s, cudaStream_t st);
+int launch_select_bwd(const SelectLaunch& s, cudaStream_t st);
+
+struct LnGroup {
+  const float* y; float* dy; int ld_y;         // plain Linear output and its gradient
+  const float* gamma; const float* beta; float* dgamma; float* dbeta;
+  float* out; const float* dout; int ld_out;   // act(LayerNorm(y))
+  float* rowstats;                             // [B][2] mean, rstd
+  int n; int act; float eps;
+};
+int launch_ln_fwd(const LnGroup* g, int n_groups, int64_t B, cudaStream_t st);
+int launch_ln_bwd(const LnGroup* g, int n_groups, int64_t B, cudaStream_t st);
+
+struct MixLaunch {
+  const float* X[16]; float* dX[16]; int ldx;          // domain-expert outputs (plain) and their gradients
+  float* out[16]; const float* dout[16]; int ldo;      // pooled outputs (accumulated into) and their gradients
+  const float* w_exp; const float* w_bal; float* dw_exp; float* dw_bal;
+  double* red;                                         // [2] scratch, zeroed by the caller
+  int D; int H; int64_t B;
+};
+int launch_mix_fwd(const MixLaunch& m, cudaStream_t st);
+int launch_mix_bwd(const MixLaunch& m, cudaStream_t st);
+
+struct BmvGroup { const float* p; float* dp; int ldp; float* q; const float* dq; int ldq; };
+struct BmvLaunch {
+  BmvGroup g[16]; int n_groups;
+  const float* H; float* dH; int ldh;                  // plain [B, k*k] and its gradient
+  int k; int accumulate_dH; int64_t B;
+};
+int launch_bmv_fwd(const BmvLaunch& m, cudaStream_t st);
+int launch_bmv_bwd(const BmvLaunch& m, cudaStream_t st);
 
 }  // namespace swr

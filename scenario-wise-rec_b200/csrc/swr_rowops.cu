@@ -209,6 +209,7 @@ struct HeadParams {
   int n_domains, dom_dtype, sig_before_select, B;
   const void* domain_id;
   float* out; const float* gout; const float* add; float* dadd;
+  int ld_add;
   float inv_count;
 };
 
@@ -217,7 +218,7 @@ __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-
 __global__ void __launch_bounds__(kRowThreads) head_fwd_kernel(const __grid_constant__ HeadParams p) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= p.B) return;
-  const int64_t d = load_index(p.domain_id, p.dom_dtype, b);
+  const int64_t d = p.sig_before_select == SWR_HEAD_NO_SELECT ? 0 : load_index(p.domain_id, p.dom_dtype, b);
   float v = 0.f;
   const bool sel = d >= 0 && d < p.n_domains;
   if (sel) {
@@ -235,8 +236,8 @@ __global__ void __launch_bounds__(kRowThreads) head_fwd_kernel(const __grid_cons
     }
   }
   float y;
-  if (p.sig_before_select) y = sel ? sigmoidf_(v) : 0.f;
-  else y = sigmoidf_(v + (p.add ? p.add[b] : 0.f));
+  if (p.sig_before_select != SWR_HEAD_SIG_SELECT_ADD) y = sel ? sigmoidf_(v) : 0.f;
+  else y = sigmoidf_(v + (p.add ? p.add[(int64_t)b * p.ld_add] : 0.f));
   p.out[b] = y;
 }
 
@@ -250,11 +251,11 @@ __global__ void __launch_bounds__(kRowThreads) head_bwd_kernel(const __grid_cons
   const int H = D.A.n;
   float dv = 0.f, dsig = 0.f;
   if (live) {
-    const int64_t di = load_index(p.domain_id, p.dom_dtype, b);
+    const int64_t di = p.sig_before_select == SWR_HEAD_NO_SELECT ? 0 : load_index(p.domain_id, p.dom_dtype, b);
     const float y = p.out[b];
     dsig = p.gout[b] * y * (1.f - y);
     if (di == d) dv = dsig;
-    if (d == 0 && !p.sig_before_select && p.dadd) p.dadd[b] = dsig;
+    if (d == 0 && p.sig_before_select == SWR_HEAD_SIG_SELECT_ADD && p.dadd) p.dadd[(int64_t)b * p.ld_add] = dsig;
   }
   const bool stats = D.A.dstats && D.A.norm.mode != SWR_NORM_NONE;
   for (int h = 0; h < H; ++h) {
@@ -283,7 +284,7 @@ static int fill_head(const HeadLaunch& l, HeadParams& p) {
   if (l.n_domains <= 0 || l.n_domains > kMaxDomains) { set_error("head: %d domains unsupported (max %d)", l.n_domains, kMaxDomains); return SWR_ERR_UNSUPPORTED; }
   for (int d = 0; d < l.n_domains; ++d) p.dom[d] = l.dom[d];
   p.n_domains = l.n_domains; p.dom_dtype = l.dom_dtype; p.sig_before_select = l.sig_before_select; p.B = (int)l.B;
-  p.domain_id = l.domain_id; p.out = l.out; p.gout = l.gout; p.add = l.add; p.dadd = l.dadd;
+  p.domain_id = l.domain_id; p.out = l.out; p.gout = l.gout; p.add = l.add; p.dadd = l.dadd; p.ld_add = l.ld_add;
   p.inv_count = 1.0f / (float)l.B;
   return SWR_OK;
 }
@@ -322,10 +323,16 @@ __global__ void __launch_bounds__(128) bn_update_kernel(const __grid_constant__ 
     double mu, var;
     col_moments(L.A.norm, c, p.inv_count, mu, var);
     // torch: running = (1 - momentum) * running + momentum * batch_stat, unbiased variance
-    if (L.rmean) L.rmean[c] = (1.f - p.momentum) * L.rmean[c] + p.momentum * (float)mu;
-    if (L.rvar) L.rvar[c] = (1.f - p.momentum) * L.rvar[c] + p.momentum * (float)(var * unbias);
+    const int rep = L.repeat > 0 ? L.repeat : 1;   // a module evaluated `rep` times on the same batch
+    float rm = L.rmean ? L.rmean[c] : 0.f, rv = L.rvar ? L.rvar[c] : 0.f;
+    for (int t = 0; t < rep; ++t) {
+      rm = (1.f - p.momentum) * rm + p.momentum * (float)mu;
+      rv = (1.f - p.momentum) * rv + p.momentum * (float)(var * unbias);
+    }
+    if (L.rmean) L.rmean[c] = rm;
+    if (L.rvar) L.rvar[c] = rv;
   }
-  if (threadIdx.x == 0 && L.nbt) *L.nbt += 1;
+  if (threadIdx.x == 0 && L.nbt) *L.nbt += (L.repeat > 0 ? L.repeat : 1);
 }
 
 __global__ void __launch_bounds__(128) bn_pgrad_kernel(const __grid_constant__ BnParams p) {

@@ -25,6 +25,10 @@ OP_ZERO, OP_GATHER, OP_SCATTER, OP_COLSTATS = 1, 2, 3, 4
 OP_FC_FWD, OP_FC_DGRAD, OP_FC_WGRAD = 5, 6, 7
 OP_POOL_FWD, OP_POOL_BWD, OP_HEAD_FWD, OP_HEAD_BWD = 8, 9, 10, 11
 OP_BN_UPDATE, OP_BN_PGRAD, OP_GROUP = 12, 13, 100
+OP_EW_FWD, OP_EW_BWD, OP_SUMGRAD, OP_SELECT_FWD, OP_SELECT_BWD = 14, 15, 16, 17, 18
+OP_LN_FWD, OP_LN_BWD, OP_MIX_FWD, OP_MIX_BWD, OP_BMV_FWD, OP_BMV_BWD = 19, 20, 21, 22, 23, 24
+EW_MUL, EW_ADD, EW_COPY = 0, 1, 2
+HEAD_SIG_SELECT_ADD, HEAD_SELECT_SIG, HEAD_NO_SELECT = 0, 1, 2
 NORM_NONE, NORM_BATCH, NORM_RUNNING = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_LEAKY = 0, 1, 2, 3
 W_NK, W_KN = 0, 1

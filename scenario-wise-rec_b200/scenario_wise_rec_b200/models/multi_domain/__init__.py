@@ -2,5 +2,8 @@
 from .sharebottom import SharedBottom
 from .mmoe import MMOE
 from .ple import PLE
+from .star import Star
+from .ppnet import PPNet
+from .epnet import EPNet
 
-__all__ = ["SharedBottom", "MMOE", "PLE"]
+__all__ = ["SharedBottom", "MMOE", "PLE", "Star", "PPNet", "EPNet"]

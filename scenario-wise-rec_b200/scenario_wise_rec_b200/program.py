@@ -44,7 +44,9 @@ class Norm:
     eps: float = 1e-5
     gamma2: Optional[torch.Tensor] = None
     beta2: Optional[torch.Tensor] = None
-    always_batch: bool = False      # STAR: batch statistics in eval mode too (star.py:95-100)
+    always_batch: bool = False      # STAR / HAMUR: batch statistics in eval mode too (star.py:95-100, hamur.py:192-195)
+    unbiased: bool = False          # HAMUR domain norm: torch.var default (divide by B - 1)
+    repeat: int = 1                 # running-stat updates per step (HAMUR evaluates its shared hyper-net once per domain)
 
 
 class Act:
@@ -59,6 +61,9 @@ class Act:
         self.needs_grad = False
         self.grad_written = False
         self.nslots: Dict[str, int] = {}
+        self.grad_cols: Optional[int] = None   # only the first grad_cols columns receive an FC data gradient
+        self.parent: Optional["Act"] = None    # column sub-view of another activation
+        self.col = 0
 
 
 @dataclass
@@ -72,6 +77,7 @@ class _FcGroup:
     layout: int = N.W_NK
     e_act: int = N.ACT_NONE
     e_scale: float = 1.0
+    detach: bool = False            # no data gradient flows back into src (x.detach() in the reference)
 
 
 @dataclass
@@ -188,21 +194,48 @@ class ProgramBuilder:
     def gather(self, sparse: Sequence[Tuple[str, torch.Tensor]], dense: Sequence[str],
                col_dtypes: Dict[str, torch.dtype]) -> Act:
         """sparse: (column name, table parameter [vocab, E]); dense: column names."""
-        n = sum(int(t.shape[1]) for _, t in sparse) + len(dense)
-        if n == 0:
-            raise ValueError("The input features can note be empty")
-        x = self.new_act(n)
+        return self.gather_parts([(sparse, dense, True)], col_dtypes)
+
+    def gather_parts(self, parts, col_dtypes: Dict[str, torch.dtype]) -> Act:
+        """Several EmbeddingLayer outputs concatenated into one activation (``torch.cat`` of
+        ppnet.py:54 / epnet.py:28).  parts: (sparse, dense, differentiable); a part with
+        differentiable=False is ``.detach()``-ed in the reference: its tables get no gradient."""
+        placed, col = [], 0
+        for sparse, dense, diff in parts:
+            n = sum(int(t.shape[1]) for _, t in sparse) + len(dense)
+            if n == 0:
+                raise ValueError("The input features can note be empty")
+            placed.append((col, list(sparse), list(dense), bool(diff)))
+            col += n
+        x = self.new_act(col)
         if self.oob_slot < 0:
             self.oob_slot = self._new_slot(("special", "oob"))
-        self.tape.append(("gather", x, list(sparse), list(dense), dict(col_dtypes)))
+        self.tape.append(("gather", x, placed, dict(col_dtypes)))
         return x
 
-    def colstats(self, src: Act, norm: Norm) -> Act:
-        """A view of ``src`` normalised with its own whole-batch statistics (STAR partitioned norm)."""
-        a = self.new_act(src.n, norm, N.ACT_NONE, raw=src.raw, ld=src.ld)
-        a.base = src
-        self.tape.append(("colstats", src, a))
+    def subview(self, src: Act, col: int, n: int) -> Act:
+        """Columns [col, col + n) of a plain activation (shares storage and gradient buffer)."""
+        if src.norm is not None or src.act != N.ACT_NONE:
+            raise NotImplementedError("subview of a lazy activation")
+        d = self.slot_desc[src.raw]
+        raw = self._new_slot(("ws32", d[1] + col, d[2] - col))
+        a = self.new_act(n, raw=raw, ld=src.ld)
+        a.parent, a.col = src, col
         return a
+
+    def colstats(self, src: Act, norms: Sequence[Norm]) -> List[Act]:
+        """Views of ``src`` normalised with its own whole-batch statistics, one per Norm (STAR
+        partitioned norm: every domain scales/shifts the same normalised input, star.py:95-100)."""
+        views = []
+        for norm in norms:
+            a = self.new_act(src.n, norm, N.ACT_NONE, raw=src.raw, ld=src.ld)
+            if views:                       # share the statistics of the first view
+                self._stats_slots.remove(a.stats)
+                a.stats = views[0].stats
+            a.base = src
+            views.append(a)
+        self.tape.append(("colstats", src, views))
+        return views
 
     def fc(self, groups: Sequence[dict]) -> List[Act]:
         """Each group: dict(src=Act, W=, b=, [W2=, b2=, layout=], norm=Norm|None, act=code, [e_act=, e_scale=])."""
@@ -216,7 +249,7 @@ class ProgramBuilder:
                 raise ValueError(f"fc: weight expects {k_in} inputs, activation has {g['src'].n}")
             out = self.new_act(n_out, g.get("norm"), g.get("act", N.ACT_NONE))
             gs.append(_FcGroup(g["src"], out, W, g.get("b"), g.get("W2"), g.get("b2"), layout,
-                               g.get("e_act", N.ACT_NONE), float(g.get("e_scale", 1.0))))
+                               g.get("e_act", N.ACT_NONE), float(g.get("e_scale", 1.0)), bool(g.get("detach", False))))
         self.tape.append(("fc", gs))
         return [g.out for g in gs]
 
@@ -242,8 +275,57 @@ class ProgramBuilder:
         self.tape.append(("pool", entries, experts, H))
         return [e[2] for e in entries]
 
+    def ew(self, mode: int, pairs, scale: float = 1.0) -> List[Act]:
+        """Element-wise op per pair (A, C): MUL -> value(A)*value(C)*scale, ADD -> value(A)+value(C),
+        COPY (C None) -> value(A) materialised.  Returns plain activations."""
+        entries = []
+        for A, C in pairs:
+            if mode != N.EW_COPY and A.n != C.n:
+                raise ValueError("ew: operand widths differ")
+            entries.append((A, C, self.new_act(A.n)))
+        self.tape.append(("ew", mode, float(scale), entries))
+        return [e[2] for e in entries]
+
+    def select(self, ys: Sequence[Act], dom_dtype: torch.dtype) -> Act:
+        """out[b] = value(ys[domain_indicator[b]])[b] (zeros for ids outside [0, D))."""
+        out = self.new_act(ys[0].n)
+        self.tape.append(("select", list(ys), out, dom_dtype))
+        return out
+
+    def layernorm(self, groups) -> List[Act]:
+        """groups: (y plain FC output, gamma, beta, eps, act code) -> act(LayerNorm(y)) plain."""
+        entries = []
+        for y, gamma, beta, eps, act in groups:
+            if y.norm is not None or y.act != N.ACT_NONE:
+                raise NotImplementedError("layernorm input must be a plain activation")
+            if y.n > 512:
+                raise NotImplementedError("LayerNorm wider than 512 is not supported by the fused kernel")
+            out = self.new_act(y.n)
+            rs = self.ws(2 * self.B)
+            self.labels[rs] = out.name + ".rowstats"
+            entries.append((y, gamma, beta, float(eps), int(act), out, rs))
+        self.tape.append(("ln", entries))
+        return [e[5] for e in entries]
+
+    def mix(self, xs: Sequence[Act], pooled: Sequence[Act], w_exp: torch.Tensor, w_bal: torch.Tensor):
+        """M3oE (m3oe.py:168-187): pooled[d] += sig(w_exp) * (sig(w_bal) * xs[d] + (1 - sig(w_bal)) / (D - 1) * sum_{j != d} xs[j])."""
+        for a in list(xs) + list(pooled):
+            if a.norm is not None or a.act != N.ACT_NONE:
+                raise NotImplementedError("mix operands must be plain activations")
+        self.tape.append(("mix", list(xs), list(pooled), w_exp, w_bal))
+
+    def bmv(self, ps: Sequence[Act], H: Act, k: int) -> List[Act]:
+        """HAMUR: q[b, :] = p[b, :] @ H[b].reshape(k, k) for every p in ps (they share H)."""
+        if H.norm is not None or H.act != N.ACT_NONE or H.n != k * k:
+            raise NotImplementedError("bmv: H must be a plain [B, k*k] activation")
+        entries = [(p_, self.new_act(k)) for p_ in ps]
+        self.tape.append(("bmv", entries, H, int(k)))
+        return [e[1] for e in entries]
+
     def head(self, domains: Sequence[Tuple[Act, Optional[torch.Tensor], Optional[torch.Tensor]]],
-             dom_dtype: torch.dtype, sig_before_select: bool = True, add: Optional[Act] = None) -> int:
+             dom_dtype: torch.dtype, sig_before_select=True, add: Optional[Act] = None) -> int:
+        """sig_before_select: True/1 select(sigmoid(v_d)); False/0 sigmoid(select(v_d) + add);
+        2 (N.HEAD_NO_SELECT) sigmoid(v_0) for every row (EPNet has no domain mask)."""
         self.out_slot = self.ws(self.B)
         self.labels[self.out_slot] = "head.out"
         self.gout_slot = self.input("__grad_out__")
@@ -274,7 +356,7 @@ class ProgramBuilder:
             s[sb + 2], s[sb + 3] = ns["rmean"], ns["rvar"]
             s[sb + 4], s[sb + 5], s[sb + 6], s[sb + 7] = ns["gamma"], ns["gamma2"], ns["beta"], ns["beta2"]
             r["f"][fb + 0] = a.norm.eps
-        r["f"][fb + 1] = 1.0
+        r["f"][fb + 1] = (self.B / (self.B - 1.0)) if (a.norm is not None and a.norm.unbiased and self.B > 1) else 1.0
         s[sb + 8], s[sb + 9] = a.dz, a.dstats
         r["i"][ib + 0], r["i"][ib + 1], r["i"][ib + 2], r["i"][ib + 3] = a.ld, a.n, a.mode, a.act
 
@@ -311,26 +393,103 @@ class ProgramBuilder:
         lo, hi = self._split64(nbytes)
         return self._hdr(N.OP_ZERO, 0, s0=slot, i0=lo, i1=hi)
 
+    def _plain_rec(self, slots: Sequence[int], ints: Sequence[int] = (), floats: Sequence[float] = ()) -> np.ndarray:
+        r = self._rec(N.OP_GROUP)
+        for i, v in enumerate(slots):
+            r["s"][i] = v
+        for i, v in enumerate(ints):
+            r["i"][i] = v
+        for i, v in enumerate(floats):
+            r["f"][i] = v
+        return r
+
+    def _act_rec(self, a: Act) -> np.ndarray:
+        r = self._rec(N.OP_GROUP)
+        self._put_act(r, a, 0, 0, 0)
+        return r
+
+    def _ew_rec(self, mode: int, scale: float, A: Act, C: Optional[Act], out: Act, flags: int = 0) -> np.ndarray:
+        r = self._rec(N.OP_GROUP)
+        self._put_act(r, A, 0, 0, 0)
+        if C is not None:
+            self._put_act(r, C, 12, 4, 2)
+        r["s"][24], r["s"][25] = out.raw, out.dz
+        r["i"][8], r["i"][9], r["i"][10] = out.ld, mode, flags
+        r["f"][4] = scale
+        return r
+
+    def _ln_rec(self, e) -> np.ndarray:
+        y, gamma, beta, eps, act, out, rs = e
+        return self._plain_rec([y.raw, y.dz, self.static(gamma), self.static(beta), self.grad(gamma), self.grad(beta),
+                                out.raw, out.dz, rs], [y.ld, y.n, out.ld, act], [eps])
+
+    def _mark_needs_grad(self):
+        """Which activations need a gradient buffer: everything downstream of a trainable input."""
+        for op in self.tape:
+            kind = op[0]
+            if kind == "gather":
+                x, parts = op[1], op[2]
+                if any(diff and any(t.requires_grad for _, t in sparse) for _c, sparse, _d, diff in parts):
+                    self._ensure_grad(x)
+            elif kind == "colstats":
+                src, views = op[1], op[2]
+                for v in views:
+                    if src.needs_grad or any(self.grad(getattr(v.norm, k)) >= 0 for k in ("gamma", "gamma2", "beta", "beta2")):
+                        self._ensure_grad(v)
+            elif kind == "fc":
+                for g in op[1]:
+                    self._ensure_grad(g.out)
+            elif kind == "pool":
+                for gate, idx, out, probs in op[1]:
+                    self._ensure_grad(out)
+            elif kind == "ew":
+                for A, C, out in op[3]:
+                    if A.needs_grad or (C is not None and C.needs_grad):
+                        self._ensure_grad(out)
+            elif kind == "select":
+                if any(y.needs_grad for y in op[1]):
+                    self._ensure_grad(op[2])
+            elif kind == "ln":
+                for e in op[1]:
+                    self._ensure_grad(e[5])
+            elif kind == "bmv":
+                for p_, q in op[1]:
+                    if p_.needs_grad or op[2].needs_grad:
+                        self._ensure_grad(q)
+        # column sub-views share their parent's gradient buffer
+        for a in self._subviews():
+            if a.parent.needs_grad and a.dz < 0:
+                d = self.slot_desc[a.parent.dz]
+                a.dz = self._new_slot(("ws32", d[1] + a.col, d[2] - a.col))
+                a.needs_grad = True
+
+    def _subviews(self) -> List[Act]:
+        seen, out = set(), []
+
+        def visit(a):
+            if a is not None and a.parent is not None and id(a) not in seen:
+                seen.add(id(a))
+                out.append(a)
+        for op in self.tape:
+            kind = op[0]
+            if kind == "fc":
+                for g in op[1]:
+                    visit(g.src)
+            elif kind == "ew":
+                for A, C, _o in op[3]:
+                    visit(A), visit(C)
+            elif kind == "head":
+                for a, _w, _b in op[1]:
+                    visit(a)
+        return out
+
     def finish(self) -> Program:
         B = self.B
         fwd: List[np.ndarray] = []
-        bwd_blocks: List[List[np.ndarray]] = []
-        # -- which activations need a gradient buffer: everything downstream of a trainable input
-        for op in self.tape:
-            if op[0] == "gather":
-                x, sparse = op[1], op[2]
-                if any(t.requires_grad for _, t in sparse):
-                    self._ensure_grad(x)
-            elif op[0] == "colstats":
-                src, a = op[1], op[2]
-                if src.needs_grad:
-                    a.dz, a.needs_grad = src.dz, True      # the view shares its base's gradient buffer
-            elif op[0] == "fc":
-                for g in op[1]:
-                    self._ensure_grad(g.out)
-            elif op[0] == "pool":
-                for gate, idx, out, probs in op[1]:
-                    self._ensure_grad(out)
+        bwd_blocks: List[list] = []
+        # sub-views must see their parent's gradient buffer before consumers are marked: two passes
+        self._mark_needs_grad()
+        self._mark_needs_grad()
         for a in self._outputs:
             if a.needs_grad:
                 if a.grad_written:
@@ -340,66 +499,67 @@ class ProgramBuilder:
             if a.needs_grad:
                 a.dstats = self.ws(2 * a.n, f64=True)
                 self.labels[a.dstats] = a.name + ".dstats"
+        dstat_slots = [a.dstats for a in self.norm_acts if a.dstats >= 0]
+        mix_red: Dict[int, int] = {}
+        for ti, op in enumerate(self.tape):
+            if op[0] == "mix":
+                mix_red[ti] = self.ws(2, f64=True)
+                dstat_slots.append(mix_red[ti])
 
-        # forward statistics region is contiguous in the f64 arena by construction? not necessarily:
-        # zero each statistics buffer range as one span from the first to the last stats slot.
+        # forward statistics: every f64 buffer allocated while building is a forward statistic -> one span
         f64_fwd = [self.slot_desc[s] for s in self._stats_slots]
         if f64_fwd:
             lo = min(d[1] for d in f64_fwd)
             hi = max(d[1] + _round_up(d[2], 2) for d in f64_fwd)
-            # all f64 buffers allocated before finish() are forward statistics -> one span
-            fwd.append(self._zero_rec(self._stats_slots[0], (hi - lo) * 8))
-            assert self.slot_desc[self._stats_slots[0]][1] == lo
-        dstat_slots = [a.dstats for a in self.norm_acts if a.dstats >= 0]
+            first = min(self._stats_slots, key=lambda s: self.slot_desc[s][1])
+            fwd.append(self._zero_rec(first, (hi - lo) * 8))
 
-        for op in self.tape:
+        for ti, op in enumerate(self.tape):
             kind = op[0]
             if kind == "gather":
-                x, sparse, dense, dts = op[1], op[2], op[3], op[4]
-                subs = []
-                col = 0
+                x, parts, dts = op[1], op[2], op[3]
                 srecs = []
-                for name, tab in sparse:
-                    r = self._rec(N.OP_GROUP)
-                    vocab, E = int(tab.shape[0]), int(tab.shape[1])
-                    r["s"][0], r["s"][1] = self.static(tab), self.input(name)
-                    r["i"][0], r["i"][1] = self._split64(vocab)
-                    r["i"][2], r["i"][3], r["i"][4], r["i"][5] = N.torch_dtype_code(dts[name]), col, 0, E
-                    subs.append(r)
-                    if tab.requires_grad:
-                        g = r.copy()
-                        g["s"][0] = self.grad(tab, "emb")
-                        srecs.append(g)
-                    col += E
-                for name in dense:
-                    r = self._rec(N.OP_GROUP)
-                    r["s"][0] = self.input(name)
-                    r["i"][2], r["i"][3], r["i"][4] = N.torch_dtype_code(dts[name]), col, 1
-                    subs.append(r)
-                    col += 1
-                fwd.append(self._hdr(N.OP_GATHER, len(subs), i1=len(sparse), i2=len(dense), i4=x.ld, s0=x.raw, s1=self.oob_slot))
-                fwd.extend(subs)
+                for col0, sparse, dense, diff in parts:
+                    subs = []
+                    col = col0
+                    for name, tab in sparse:
+                        r = self._rec(N.OP_GROUP)
+                        vocab, E = int(tab.shape[0]), int(tab.shape[1])
+                        r["s"][0], r["s"][1] = self.static(tab), self.input(name)
+                        r["i"][0], r["i"][1] = self._split64(vocab)
+                        r["i"][2], r["i"][3], r["i"][4], r["i"][5] = N.torch_dtype_code(dts[name]), col, 0, E
+                        subs.append(r)
+                        if tab.requires_grad and diff:
+                            g = r.copy()
+                            g["s"][0] = self.grad(tab, "emb")
+                            srecs.append(g)
+                        col += E
+                    for name in dense:
+                        r = self._rec(N.OP_GROUP)
+                        r["s"][0] = self.input(name)
+                        r["i"][2], r["i"][3], r["i"][4] = N.torch_dtype_code(dts[name]), col, 1
+                        subs.append(r)
+                        col += 1
+                    fwd.append(self._hdr(N.OP_GATHER, len(subs), i1=len(sparse), i2=len(dense), i4=x.ld, i5=col0,
+                                         s0=x.raw, s1=self.oob_slot))
+                    fwd.extend(subs)
                 if srecs and x.needs_grad:
                     bwd_blocks.append([self._hdr(N.OP_SCATTER, len(srecs), i1=len(srecs), i4=x.ld, s0=x.dz)] + srecs)
             elif kind == "colstats":
-                src, a = op[1], op[2]
-                fwd.append(self._hdr(N.OP_COLSTATS, 0, i1=src.n, i2=src.ld, s0=src.raw, s1=a.stats))
-                # backward: consumers wrote dz (stage 1 w.r.t. the normalised view) into the shared buffer;
-                # the stage-2 correction back to the raw tensor is applied by op "dn_bwd" (STAR only)
-                bwd_blocks.append([("dn_bwd", src, a)])
+                src, views = op[1], op[2]
+                fwd.append(self._hdr(N.OP_COLSTATS, 0, i1=src.n, i2=src.ld, s0=src.raw, s1=views[0].stats))
+                if src.needs_grad:
+                    bwd_blocks.append([("sumgrad", src, views)])
             elif kind == "fc":
                 gs = op[1]
                 fwd.append(self._hdr(N.OP_FC_FWD, len(gs)))
                 fwd.extend(self._fc_rec(g) for g in gs)
-                blk: List[np.ndarray] = []
-                blk.append(self._hdr(N.OP_FC_WGRAD, len(gs)))
-                blk.extend(self._fc_rec(g) for g in gs)
+                blk: list = [("wgrad", gs)]
                 # one fan-in dgrad per distinct input activation that needs a gradient
                 by_src: Dict[int, List[_FcGroup]] = {}
                 for g in gs:
-                    if g.src.needs_grad:
+                    if g.src.needs_grad and not g.detach:
                         by_src.setdefault(id(g.src), []).append(g)
-                self._pending_dgrad = getattr(self, "_pending_dgrad", [])
                 for lst in by_src.values():
                     blk.append(("dgrad", lst))
                 bwd_blocks.append(blk)
@@ -415,23 +575,50 @@ class ProgramBuilder:
                     r["i"][16:16 + len(idx)] = idx
                     subs.append(r)
                 for e in experts:
-                    r = self._rec(N.OP_GROUP)
-                    self._put_act(r, e, 0, 0, 0)
-                    subs.append(r)
+                    subs.append(self._act_rec(e))
                 fwd.append(self._hdr(N.OP_POOL_FWD, len(subs), i1=H, i2=len(entries), i3=len(experts)))
                 fwd.extend(subs)
                 bwd_blocks.append([("pool_bwd", entries, experts, H)])
+            elif kind == "ew":
+                mode, scale, entries = op[1], op[2], op[3]
+                fwd.append(self._hdr(N.OP_EW_FWD, len(entries)))
+                fwd.extend(self._ew_rec(mode, scale, A, C, out) for A, C, out in entries)
+                bwd_blocks.append([("ew_bwd", mode, scale, entries)])
+            elif kind == "select":
+                ys, out, dom_dtype = op[1], op[2], op[3]
+                fwd.append(self._hdr(N.OP_SELECT_FWD, len(ys), i1=out.n, i2=out.ld, i3=N.torch_dtype_code(dom_dtype),
+                                     s0=self.input("domain_indicator"), s1=out.raw, s2=-1))
+                fwd.extend(self._act_rec(y) for y in ys)
+                bwd_blocks.append([("select_bwd", ys, out, dom_dtype)])
+            elif kind == "ln":
+                entries = op[1]
+                fwd.append(self._hdr(N.OP_LN_FWD, len(entries)))
+                fwd.extend(self._ln_rec(e) for e in entries)
+                bwd_blocks.append([("ln_bwd", entries)])
+            elif kind == "mix":
+                xs, pooled, w_exp, w_bal = op[1], op[2], op[3], op[4]
+                subs = [self._plain_rec([x.raw, -1, o.raw, -1]) for x, o in zip(xs, pooled)]
+                fwd.append(self._hdr(N.OP_MIX_FWD, len(subs), i1=len(xs), i2=xs[0].n, i3=xs[0].ld, i4=pooled[0].ld,
+                                     s0=self.static(w_exp), s1=self.static(w_bal), s2=-1, s3=-1, s4=-1))
+                fwd.extend(subs)
+                bwd_blocks.append([("mix_bwd", xs, pooled, w_exp, w_bal, mix_red[ti])])
+            elif kind == "bmv":
+                entries, H, k = op[1], op[2], op[3]
+                fwd.append(self._hdr(N.OP_BMV_FWD, len(entries), i1=k, i2=H.ld, i3=0, s0=H.raw, s1=-1))
+                fwd.extend(self._plain_rec([p_.raw, -1, q.raw, -1], [p_.ld, q.ld]) for p_, q in entries)
+                bwd_blocks.append([("bmv_bwd", entries, H, k)])
             elif kind == "head":
                 domains, dom_dtype, sbs, add = op[1], op[2], op[3], op[4]
                 subs = []
                 for a, w, b in domains:
-                    r = self._rec(N.OP_GROUP)
-                    self._put_act(r, a, 0, 0, 0)
+                    r = self._act_rec(a)
                     r["s"][24], r["s"][26] = self.static(w), self.static(b)
                     subs.append(r)
-                hdr = self._hdr(N.OP_HEAD_FWD, len(subs), i1=len(subs), i2=int(sbs), i3=N.torch_dtype_code(dom_dtype),
-                                s0=self.input("domain_indicator"), s1=self.out_slot, s2=-1,
-                                s3=(add.raw if add is not None else -1), s4=-1)
+                no_sel = int(sbs) == N.HEAD_NO_SELECT
+                hdr = self._hdr(N.OP_HEAD_FWD, len(subs), i1=len(subs), i2=int(sbs),
+                                i3=N.DT_I64 if no_sel else N.torch_dtype_code(dom_dtype),
+                                s0=-1 if no_sel else self.input("domain_indicator"), s1=self.out_slot, s2=-1,
+                                s3=(add.raw if add is not None else -1), s4=-1, i4=(add.ld if add is not None else 1))
                 fwd.append(hdr)
                 fwd.extend(subs)
                 bwd_blocks.append([("head_bwd", domains, dom_dtype, sbs, add)])
@@ -441,9 +628,9 @@ class ProgramBuilder:
             if bn:
                 subs = []
                 for a in bn:
-                    r = self._rec(N.OP_GROUP)
-                    self._put_act(r, a, 0, 0, 0)
+                    r = self._act_rec(a)
                     r["s"][24] = self.static(a.norm.nbt)
+                    r["i"][8] = int(a.norm.repeat)
                     subs.append(r)
                 fwd.append(self._hdr(N.OP_BN_UPDATE, len(subs), f4=0.1))
                 fwd.extend(subs)
@@ -456,6 +643,16 @@ class ProgramBuilder:
             hi = max(d[1] + _round_up(d[2], 2) for d in descs)
             first = min(dstat_slots, key=lambda s: self.slot_desc[s][1])
             bwd.append(self._zero_rec(first, (hi - lo) * 8))
+
+        def first_write(a: Act) -> bool:
+            """True if this is the first gradient written into ``a`` (later writers accumulate)."""
+            root = a.parent if a.parent is not None else a
+            acc = a.grad_written
+            a.grad_written = True
+            if a.parent is not None:
+                root.partial_written = True
+            return not acc
+
         for blk in reversed(bwd_blocks):
             for item in blk:
                 if isinstance(item, np.ndarray):
@@ -466,31 +663,29 @@ class ProgramBuilder:
                     _, domains, dom_dtype, sbs, add = item
                     subs = []
                     for a, w, b in domains:
-                        if a.grad_written:
+                        if not first_write(a):
                             raise NotImplementedError("head: a tower output consumed twice")
-                        a.grad_written = True
-                        r = self._rec(N.OP_GROUP)
-                        self._put_act(r, a, 0, 0, 0)
+                        r = self._act_rec(a)
                         r["s"][24], r["s"][26] = self.static(w), self.static(b)
                         r["s"][28], r["s"][30] = self.grad(w), self.grad(b)
                         subs.append(r)
                     dadd = -1
                     if add is not None and add.needs_grad:
-                        if add.grad_written:
+                        if not first_write(add):
                             raise NotImplementedError("head: additive term consumed twice")
-                        add.grad_written = True
                         dadd = add.dz
-                    bwd.append(self._hdr(N.OP_HEAD_BWD, len(subs), i1=len(subs), i2=int(sbs), i3=N.torch_dtype_code(dom_dtype),
-                                         s0=self.input("domain_indicator"), s1=self.out_slot, s2=self.gout_slot,
-                                         s3=(add.raw if add is not None else -1), s4=dadd))
+                    no_sel = int(sbs) == N.HEAD_NO_SELECT
+                    bwd.append(self._hdr(N.OP_HEAD_BWD, len(subs), i1=len(subs), i2=int(sbs),
+                                         i3=N.DT_I64 if no_sel else N.torch_dtype_code(dom_dtype),
+                                         s0=-1 if no_sel else self.input("domain_indicator"), s1=self.out_slot, s2=self.gout_slot,
+                                         s3=(add.raw if add is not None else -1), s4=dadd, i4=(add.ld if add is not None else 1)))
                     bwd.extend(subs)
                 elif tag == "pool_bwd":
                     _, entries, experts, H = item
                     subs = []
                     for gate, idx, out, probs in entries:
-                        if gate.grad_written:
+                        if not first_write(gate):
                             raise NotImplementedError("pool: gate logits consumed twice")
-                        gate.grad_written = True
                         r = self._rec(N.OP_GROUP)
                         self._put_act(r, gate, 0, 0, 0)
                         self._put_act(r, out, 12, 4, 2)
@@ -499,38 +694,98 @@ class ProgramBuilder:
                         r["i"][16:16 + len(idx)] = idx
                         subs.append(r)
                     for e in experts:
-                        if e.grad_written:
+                        if not first_write(e):
                             raise NotImplementedError("pool: expert output consumed by two pooling ops")
-                        e.grad_written = True
-                        r = self._rec(N.OP_GROUP)
-                        self._put_act(r, e, 0, 0, 0)
-                        subs.append(r)
+                        subs.append(self._act_rec(e))
                     bwd.append(self._hdr(N.OP_POOL_BWD, len(subs), i1=H, i2=len(entries), i3=len(experts)))
                     bwd.extend(subs)
+                elif tag == "wgrad":
+                    gs = item[1]
+                    bwd.append(self._hdr(N.OP_FC_WGRAD, len(gs)))
+                    bwd.extend(self._fc_rec(g) for g in gs)
                 elif tag == "dgrad":
                     lst = item[1]
                     src = lst[0].src
-                    flags = 1 | (2 if src.grad_written else 0)
-                    src.grad_written = True
+                    flags = 1 | (0 if first_write(src) else 2)
                     bwd.append(self._hdr(N.OP_FC_DGRAD, len(lst)))
-                    bwd.extend(self._fc_rec(g, flags) for g in lst)
-                elif tag == "dn_bwd":
-                    raise NotImplementedError("partitioned-norm backward is emitted by the STAR builder")
+                    for g in lst:
+                        r = self._fc_rec(g, flags)
+                        if src.grad_cols is not None:
+                            r["i"][1] = src.grad_cols        # narrower destination: only these columns get dA
+                        bwd.append(r)
+                elif tag == "sumgrad":
+                    _, src, views = item
+                    live = [v for v in views if v.needs_grad]
+                    acc = 0 if first_write(src) else 1
+                    bwd.append(self._hdr(N.OP_SUMGRAD, 1 + len(live), i1=acc))
+                    bwd.append(self._act_rec(src))
+                    bwd.extend(self._act_rec(v) for v in live)
+                elif tag == "ew_bwd":
+                    _, mode, scale, entries = item
+                    subs = []
+                    for A, C, out in entries:
+                        if not out.needs_grad:
+                            continue
+                        flags = 0
+                        if A.needs_grad:
+                            flags |= 1 | (0 if first_write(A) else 4)
+                        if C is not None and C.needs_grad:
+                            flags |= 2 | (0 if first_write(C) else 8)
+                        subs.append(self._ew_rec(mode, scale, A, C, out, flags))
+                    if subs:
+                        bwd.append(self._hdr(N.OP_EW_BWD, len(subs)))
+                        bwd.extend(subs)
+                elif tag == "select_bwd":
+                    _, ys, out, dom_dtype = item
+                    if out.needs_grad:
+                        for y in ys:
+                            if not first_write(y):
+                                raise NotImplementedError("select: an input consumed twice")
+                        bwd.append(self._hdr(N.OP_SELECT_BWD, len(ys), i1=out.n, i2=out.ld, i3=N.torch_dtype_code(dom_dtype),
+                                             s0=self.input("domain_indicator"), s1=out.raw, s2=out.dz))
+                        bwd.extend(self._act_rec(y) for y in ys)
+                elif tag == "ln_bwd":
+                    entries = item[1]
+                    for e in entries:
+                        if not first_write(e[0]):
+                            raise NotImplementedError("layernorm: input consumed twice")
+                    bwd.append(self._hdr(N.OP_LN_BWD, len(entries)))
+                    bwd.extend(self._ln_rec(e) for e in entries)
+                elif tag == "mix_bwd":
+                    _, xs, pooled, w_exp, w_bal, red = item
+                    for x in xs:
+                        if not first_write(x):
+                            raise NotImplementedError("mix: a domain expert output consumed twice")
+                    subs = [self._plain_rec([x.raw, x.dz, o.raw, o.dz]) for x, o in zip(xs, pooled)]
+                    bwd.append(self._hdr(N.OP_MIX_BWD, len(subs), i1=len(xs), i2=xs[0].n, i3=xs[0].ld, i4=pooled[0].ld,
+                                         s0=self.static(w_exp), s1=self.static(w_bal), s2=self.grad(w_exp), s3=self.grad(w_bal), s4=red))
+                    bwd.extend(subs)
+                elif tag == "bmv_bwd":
+                    _, entries, H, k = item
+                    live = [(p_, q) for p_, q in entries if q.needs_grad]
+                    if live:
+                        for p_, _q in live:
+                            if p_.needs_grad and not first_write(p_):
+                                raise NotImplementedError("bmv: an input vector consumed twice")
+                        acc = 0
+                        if H.needs_grad:
+                            acc = 0 if first_write(H) else 1
+                        bwd.append(self._hdr(N.OP_BMV_BWD, len(live), i1=k, i2=H.ld, i3=acc, s0=H.raw, s1=(H.dz if H.needs_grad else -1)))
+                        bwd.extend(self._plain_rec([p_.raw, p_.dz if p_.needs_grad else -1, q.raw, q.dz], [p_.ld, q.ld]) for p_, q in live)
         pg = [a for a in self.norm_acts if a.needs_grad and a.dstats >= 0 and
               (self.grad(a.norm.gamma) >= 0 or self.grad(a.norm.beta) >= 0 or
                self.grad(a.norm.gamma2) >= 0 or self.grad(a.norm.beta2) >= 0)]
         if pg:
             subs = []
             for a in pg:
-                r = self._rec(N.OP_GROUP)
-                self._put_act(r, a, 0, 0, 0)
+                r = self._act_rec(a)
                 r["s"][24], r["s"][25] = self.grad(a.norm.gamma), self.grad(a.norm.gamma2)
                 r["s"][26], r["s"][27] = self.grad(a.norm.beta), self.grad(a.norm.beta2)
                 subs.append(r)
-            # parameter gradients of the norms need the complete backward sums -> after every dgrad,
-            # but before the scatter is irrelevant; append at the end
             bwd.append(self._hdr(N.OP_BN_PGRAD, len(subs)))
             bwd.extend(subs)
+        # the scatter blocks were emitted in place (they are np records inside bwd_blocks) -- they run after every
+        # writer of x.dz because the gather is the first tape entry of its activation.
 
         def stack(lst):
             return np.stack(lst).astype(N.REC_DTYPE) if lst else np.zeros((0,), dtype=N.REC_DTYPE)

@@ -75,7 +75,7 @@ def test_every_buffer_matches_interpreter(name, training):
     for p, a, b in zip(rc.prog.params, gc, gr):
         scale = max(float(b.abs().max()), 1e-3)
         err = float((a.cpu() - b).abs().max())
-        assert err <= 2e-4 * scale, f"param grad {tuple(p.shape)} err {err} scale {scale}"
+        assert err <= 2e-4 * scale + 1e-6, f"param grad {tuple(p.shape)} err {err} scale {scale}"
 
 
 def _prog(model, x):
