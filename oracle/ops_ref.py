@@ -493,7 +493,8 @@ class RefRunner:
     def _ln_decode(self, r):
         s, i = r["s"], r["i"]
         ld_y, n, ld_o, act = int(i[0]), int(i[1]), int(i[2]), int(i[3])
-        vec = lambda k: None if s[k] < 0 else self.slot(int(s[k])).reshape(-1)[:n]      # noqa: E731
+        # gradient slots are unbound during the forward pass
+        vec = lambda k: None if (s[k] < 0 or self.tensors[int(s[k])] is None) else self.slot(int(s[k])).reshape(-1)[:n]      # noqa: E731
         rs = self.slot(int(s[8]))[:2 * self.prog.B].view(self.prog.B, 2)
         return (self._plain(s[0], ld_y, n), self._plain(s[1], ld_y, n), vec(2), vec(3), vec(4), vec(5),
                 self._plain(s[6], ld_o, n), self._plain(s[7], ld_o, n), rs, act, float(r["f"][0]))

@@ -5,5 +5,7 @@ from .ple import PLE
 from .star import Star
 from .ppnet import PPNet
 from .epnet import EPNet
+from .hamur import HamurLarge, HamurSmall
+from .m3oe import M3oE
 
-__all__ = ["SharedBottom", "MMOE", "PLE", "Star", "PPNet", "EPNet"]
+__all__ = ["SharedBottom", "MMOE", "PLE", "Star", "PPNet", "EPNet", "HamurLarge", "HamurSmall", "M3oE"]
