@@ -148,6 +148,8 @@ typedef enum swr_op_kind {
   SWR_OP_MIX_BWD = 22,
   SWR_OP_BMV_FWD = 23,    /* HAMUR per-sample q[b,:] = p[b,:] * H_b (hamur.py:177-189)   */
   SWR_OP_BMV_BWD = 24,
+  SWR_OP_BCE = 25,        /* BCELoss forward (mean) + d loss / d prediction (ctr_trainer.py:70) */
+  SWR_OP_ADAM = 26,       /* torch.optim.Adam over flat param/grad/moment arenas (ctr_trainer.py:73) */
   SWR_OP_GROUP = 100      /* a group record belonging to the preceding header          */
 } swr_op_kind;
 
@@ -164,6 +166,10 @@ enum { SWR_HEAD_SELECT_SIG = 1, SWR_HEAD_SIG_SELECT_ADD = 0, SWR_HEAD_NO_SELECT 
 
 SWR_API int swr_program_run(const swr_rec_t* recs, int32_t n_recs, void* const* slots,
                     int32_t n_slots, void* stream);
+
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream): the trainer's single H2D copy of a
+ * packed batch (pinned host staging -> device staging) and the D2H read-back of the loss ring. */
+SWR_API int swr_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -582,3 +582,26 @@ class RefRunner:
                 dH += tot
             else:
                 dH.copy_(tot)
+
+    # -- trainer-side ops (csrc/swr_train.cu) ---------------------------------------------------------------
+    def _op_25(self, h, subs):      # BCE
+        B, ring = int(h["i"][0]), max(int(h["i"][2]), 1)
+        p = self.slot(int(h["s"][0])).reshape(-1)[:B]
+        y = self.slot(int(h["s"][1])).reshape(-1)[:B].float()
+        lp, l1p = torch.log(p).clamp_min(-100.0), torch.log(1 - p).clamp_min(-100.0)
+        if h["s"][2] >= 0:
+            self.slot(int(h["s"][2])).reshape(-1)[:B].copy_((p - y) / ((1 - p) * p).clamp_min(1e-12) / B)
+        if h["s"][3] >= 0:
+            idx = int(self.slot(int(h["s"][4])).reshape(-1)[0]) % ring if h["s"][4] >= 0 else 0
+            self.slot(int(h["s"][3])).reshape(-1)[idx] = -(y * lp + (1 - y) * l1p).double().mean().float()
+
+    def _op_26(self, h, subs):      # ADAM
+        n = self._i64(h["i"][0], h["i"][1])
+        p, g, m, v = (self.slot(int(h["s"][k])).reshape(-1)[:n] for k in range(4))
+        step_size, b1, b2, eps, wd, ibc2 = (float(t) for t in self.slot(int(h["s"][4])).reshape(-1)[:6])
+        gg = g + wd * p
+        m.copy_(m + (1 - b1) * (gg - m))
+        v.copy_(b2 * v + (1 - b2) * gg * gg)
+        p.sub_(step_size * m / (v.sqrt() * ibc2 + eps))
+        if int(h["i"][2]):
+            g.zero_()

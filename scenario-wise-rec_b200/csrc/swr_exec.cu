@@ -364,6 +364,15 @@ SWR_API int swr_program_run(const swr_rec_t* recs, int32_t n_recs, void* const* 
       case SWR_OP_MIX_BWD: rc = run_mix(h, subs, true, c, st); break;
       case SWR_OP_BMV_FWD: rc = run_bmv(h, subs, false, c, st); break;
       case SWR_OP_BMV_BWD: rc = run_bmv(h, subs, true, c, st); break;
+      case SWR_OP_BCE:
+        rc = launch_bce(static_cast<const float*>(c.slot(h.s[0])), c.slot(h.s[1]), h.i[1], static_cast<float*>(c.slot(h.s[2])),
+                        static_cast<float*>(c.slot(h.s[3])), static_cast<const int32_t*>(c.slot(h.s[4])), h.i[2], h.i[0], st);
+        break;
+      case SWR_OP_ADAM:
+        rc = launch_adam(static_cast<float*>(c.slot(h.s[0])), static_cast<float*>(c.slot(h.s[1])), static_cast<float*>(c.slot(h.s[2])),
+                         static_cast<float*>(c.slot(h.s[3])), static_cast<const float*>(c.slot(h.s[4])),
+                         ((int64_t)(uint32_t)h.i[0]) | ((int64_t)h.i[1] << 32), h.i[2], st);
+        break;
       default: set_error("program: unknown op kind %d at record %d", h.kind, i); return SWR_ERR_INVALID;
     }
     if (prof) { cudaEventRecord(pe.e1, st); std::lock_guard<std::mutex> lk(g_prof_mu); g_prof.push_back(pe); }
@@ -371,6 +380,14 @@ SWR_API int swr_program_run(const swr_rec_t* recs, int32_t n_recs, void* const* 
     if (rc) return rc;
     i += 1 + h.n_sub;
   }
+  return SWR_OK;
+}
+
+SWR_API int swr_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream) {
+  g_err[0] = 0;
+  if (bytes < 0 || (bytes > 0 && (!dst || !src))) { set_error("memcpy: bad argument"); return SWR_ERR_INVALID; }
+  if (bytes == 0) return SWR_OK;
+  SWR_CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
   return SWR_OK;
 }
 

@@ -27,6 +27,7 @@ OP_POOL_FWD, OP_POOL_BWD, OP_HEAD_FWD, OP_HEAD_BWD = 8, 9, 10, 11
 OP_BN_UPDATE, OP_BN_PGRAD, OP_GROUP = 12, 13, 100
 OP_EW_FWD, OP_EW_BWD, OP_SUMGRAD, OP_SELECT_FWD, OP_SELECT_BWD = 14, 15, 16, 17, 18
 OP_LN_FWD, OP_LN_BWD, OP_MIX_FWD, OP_MIX_BWD, OP_BMV_FWD, OP_BMV_BWD = 19, 20, 21, 22, 23, 24
+OP_BCE, OP_ADAM = 25, 26
 EW_MUL, EW_ADD, EW_COPY = 0, 1, 2
 HEAD_SIG_SELECT_ADD, HEAD_SELECT_SIG, HEAD_NO_SELECT = 0, 1, 2
 NORM_NONE, NORM_BATCH, NORM_RUNNING = 0, 1, 2
@@ -36,7 +37,7 @@ W_NK, W_KN = 0, 1
 DT_I8, DT_I16, DT_I32, DT_I64, DT_U8, DT_F16, DT_BF16, DT_F32, DT_F64 = 0, 1, 2, 3, 4, 8, 9, 10, 11
 
 EXPORTS = ("swr_abi_version", "swr_last_error", "swr_launch_count", "swr_device_check",
-           "swr_profile_begin", "swr_profile_end",
+           "swr_profile_begin", "swr_profile_end", "swr_memcpy_async",
            "swr_embedding_gather_fwd", "swr_embedding_scatter_bwd", "swr_program_run")
 
 _lib = None
@@ -63,6 +64,8 @@ def lib():
     L.swr_embedding_gather_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, vp, vp]
     L.swr_embedding_scatter_bwd.restype = ctypes.c_int
     L.swr_embedding_scatter_bwd.argtypes = [vp, i64, i64, vp, vp, vp, vp, i32, i32, vp]
+    L.swr_memcpy_async.restype = ctypes.c_int
+    L.swr_memcpy_async.argtypes = [vp, vp, i64, vp]
     L.swr_profile_begin.restype = ctypes.c_int
     L.swr_profile_end.restype = ctypes.c_int
     L.swr_profile_end.argtypes = [vp, vp, vp, i32]
@@ -91,6 +94,10 @@ def program_run(recs: np.ndarray, slots: np.ndarray, stream: int):
     assert slots.dtype == np.uint64 and slots.flags.c_contiguous
     st = lib().swr_program_run(recs.ctypes.data, recs.shape[0], slots.ctypes.data, slots.shape[0], stream)
     check(st, "swr_program_run")
+
+
+def memcpy_async(dst: int, src: int, nbytes: int, stream: int):
+    check(lib().swr_memcpy_async(dst, src, nbytes, stream), "swr_memcpy_async")
 
 
 def profile_begin():

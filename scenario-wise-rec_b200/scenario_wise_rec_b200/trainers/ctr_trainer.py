@@ -6,6 +6,12 @@
 the evaluation methods return the same values.  The per-batch work is delegated to
 :meth:`train_step`, which callers (bench.py) may also drive directly with one
 ``(x_dict, y)`` batch of host or device tensors.
+
+When the model is one of this package's device-program models on a CUDA device and the
+optimizer is plain ``torch.optim.Adam`` (the trainer default), ``train_step`` runs the whole
+step -- forward, BCELoss, backward, Adam -- as ONE CUDA graph fed by one packed H2D copy
+(:mod:`.fused_step`); same arithmetic, same ``state_dict`` / ``optimizer.state`` contents.
+Any other combination takes the reference loop verbatim.  ``fused=False`` forces the latter.
 """
 from __future__ import annotations
 
@@ -27,8 +33,13 @@ def _progress(it, desc):
 
 class CTRTrainer(object):
     def __init__(self, model, data_set_type, optimizer_fn=torch.optim.Adam, optimizer_params=None, scheduler_fn=None,
-                 scheduler_params=None, n_epoch=10, earlystop_patience=10, device="cpu", gpus=None, model_path="./"):
+                 scheduler_params=None, n_epoch=10, earlystop_patience=10, device="cpu", gpus=None, model_path="./",
+                 fused=True):
         self.model = model
+        self.fused = fused
+        self._steps = {}
+        self._flat = None
+        self._grad_sync = None
         self.data_set_type = data_set_type
         gpus = [] if gpus is None else gpus
         self.gpus = gpus
@@ -61,6 +72,8 @@ class CTRTrainer(object):
 
         self.model._grad_sync = sync
         self.model._programs = {}
+        self._grad_sync = sync
+        self._steps = {}
 
     @staticmethod
     def evaluate_fn(targets, predicts):
@@ -68,8 +81,44 @@ class CTRTrainer(object):
         return roc_auc_score(targets, predicts)
 
     # ---- one batch -----------------------------------------------------------------------------
-    def train_step(self, x_dict, y):
-        """ctr_trainer.py:67-73 for one batch; returns the loss tensor (device, not synchronised)."""
+    def _fused_step_for(self, x_dict):
+        from ..fused import FusedModule
+        from .fused_step import FlatArenas, FusedTrainStep, PackedBatch, adam_supported
+        if not (self.fused and isinstance(self.model, FusedModule) and self.device.type == "cuda" and self.model.training
+                and adam_supported(self.optimizer) and type(self.criterion) is torch.nn.BCELoss
+                and self.criterion.reduction == "mean" and self.criterion.weight is None):
+            return None
+        if self._flat is not None and not self._flat.valid():
+            self._flat, self._steps = None, {}           # parameter storage was replaced (model.to / .float ...)
+        if isinstance(x_dict, PackedBatch):
+            key = x_dict.key
+        else:
+            cols = self.model._columns()
+            key = (int(x_dict[cols[0]].shape[0]), tuple(x_dict[c].dtype for c in cols))
+        fs = self._steps.get(key)
+        if fs is None:
+            if isinstance(x_dict, PackedBatch):
+                raise ValueError("no fused step was built for this packed batch; call trainer.packer(x_dict) first")
+            fs = FusedTrainStep(self.model, self.optimizer, x_dict, self.device, flat=self._flat, grad_sync=self._grad_sync)
+            if self._flat is None:
+                self._flat = fs.flat
+                self.optimizer.register_state_dict_pre_hook(lambda _opt: self._flat is not None and self._flat.publish_step())
+            self._steps[key] = fs
+        return fs
+
+    def packer(self, x_dict):
+        """The fused step object for batches shaped like ``x_dict``: ``packer(x).pack(x, y, device)`` lays a batch out
+        in the staging format once, so ``train_step(packed)`` is a single copy + one graph launch."""
+        fs = self._fused_step_for(x_dict)
+        if fs is None:
+            raise RuntimeError("the fused training step is not available for this model / optimizer / device")
+        return fs
+
+    def train_step(self, x_dict, y=None):
+        """ctr_trainer.py:67-73 for one batch; returns the loss (``.item()`` reads it; device work is not synchronised)."""
+        fs = self._fused_step_for(x_dict)
+        if fs is not None:
+            return fs.step(x_dict, y)
         x_dict = {k: v.to(self.device, non_blocking=True) for k, v in x_dict.items()}
         y = y.to(self.device, non_blocking=True)
         y_pred = self.model(x_dict)
@@ -83,13 +132,23 @@ class CTRTrainer(object):
         self.model.train()
         total_loss = 0
         tk0 = _progress(data_loader, "train")
+        pending = []
         for i, (x_dict, y) in enumerate(tk0):
-            loss = self.train_step(x_dict, y)
-            total_loss += loss.item()
+            pending.append(self.train_step(x_dict, y))
             if (i + 1) % log_interval == 0:
+                # the reference adds loss.item() every step (a host sync per batch); the same running mean is
+                # formed here once per log interval so the device never waits for the host in between
+                total_loss = sum(l.item() for l in pending)
+                pending = []
                 if hasattr(tk0, "set_postfix"):
                     tk0.set_postfix(loss=total_loss / log_interval)
                 total_loss = 0
+        for l in pending:
+            l.item()
+        if self._flat is not None:
+            self._flat.publish_step()
+        if hasattr(self.model, "check_indices"):
+            self.model.check_indices()
 
     def fit(self, train_dataloader, val_dataloader=None):
         for epoch_i in range(self.n_epoch):

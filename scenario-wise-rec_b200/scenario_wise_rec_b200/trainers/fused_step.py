@@ -1,0 +1,323 @@
+"""One CUDA graph per training step.
+
+``CTRTrainer.train_step`` (reference loop: trainers/ctr_trainer.py:67-73) maps onto
+
+    host   pack the batch columns into one pinned staging buffer          (no per-column H2D copies)
+    H2D    ONE cudaMemcpyAsync of the packed batch + 64 B of per-step scalars
+    graph  forward program -> BCELoss fwd/grad -> zero gradient arenas -> backward program
+           (-> NCCL all-reduce of the arenas under data parallel) -> Adam over the flat arenas
+           -> D2H copy of the loss ring
+    host   the loss of step k is read from the pinned ring when the caller asks for it
+
+Parameters stay ordinary ``nn.Parameter`` objects under the reference's names; their storage is
+re-pointed into flat arenas (one for the tower / expert / gate weights, one for the embedding
+tables) laid out like the program's gradient arenas, so the optimizer is a single streaming
+kernel per arena.  ``optimizer.state`` holds views of the flat moment arenas: ``state_dict()`` /
+``load_state_dict()`` of model and optimizer keep working.  Semantics are torch.optim.Adam's
+(dense gradients, L2 weight decay on every row of every table, every step).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .. import _native as N
+from ..program import CudaRunner, Program, ProgramBuilder
+
+_NP = {torch.int8: np.int8, torch.int16: np.int16, torch.int32: np.int32, torch.int64: np.int64, torch.uint8: np.uint8,
+       torch.float16: np.float16, torch.float32: np.float32, torch.float64: np.float64, torch.bool: np.bool_}
+RING = 64          # loss ring / per-step scalar ring
+NSTAGE = 4         # rotating pinned staging buffers
+
+
+def adam_supported(opt) -> bool:
+    if type(opt) is not torch.optim.Adam or len(opt.param_groups) != 1:
+        return False
+    g = opt.param_groups[0]
+    return not (g.get("amsgrad") or g.get("maximize") or g.get("differentiable") or g.get("capturable"))
+
+
+def _align(n: int, a: int = 16) -> int:
+    return (n + a - 1) // a * a
+
+
+class FlatArenas:
+    """Flat parameter / gradient / Adam-moment storage shared by every program of one model."""
+
+    def __init__(self, prog: Program, optimizer, device):
+        self.device = device
+        self.layout = [(id(p), a, off, n) for p, (a, off, n) in zip(prog.params, prog.param_arena)]
+        self.size = {k: max(v, 4) for k, v in prog.arena_size.items()}
+        z = lambda k: torch.zeros(self.size[k], dtype=torch.float32, device=device)      # noqa: E731
+        self.p = {k: z(k) for k in self.size}
+        self.g = {k: z(k) for k in self.size}
+        self.m = {k: z(k) for k in self.size}
+        self.v = {k: z(k) for k in self.size}
+        self.params = list(prog.params)
+        step = 0
+        with torch.no_grad():
+            for p, (a, off, n) in zip(prog.params, prog.param_arena):
+                if p.device != device or p.dtype != torch.float32:
+                    raise RuntimeError("parameters must be float32 on the trainer's device")
+                flat = self.p[a][off:off + n]
+                flat.copy_(p.data.reshape(-1))
+                p.data = flat.view(p.shape)
+                p.grad = self.g[a][off:off + n].view(p.shape)
+                st = optimizer.state.get(p)
+                if st and "exp_avg" in st:
+                    self.m[a][off:off + n].copy_(st["exp_avg"].reshape(-1))
+                    self.v[a][off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                    step = max(step, int(st["step"]))
+                optimizer.state[p] = {"step": torch.tensor(float(step)), "exp_avg": self.m[a][off:off + n].view(p.shape),
+                                      "exp_avg_sq": self.v[a][off:off + n].view(p.shape)}
+        self.step = step
+        self.optimizer = optimizer
+        self._ptr0 = [p.data_ptr() for p in self.params[:1] + self.params[-1:]]
+
+    def valid(self) -> bool:
+        """False after ``model.to()`` / ``load`` replaced parameter storage behind our back."""
+        return [p.data_ptr() for p in self.params[:1] + self.params[-1:]] == self._ptr0
+
+    def matches(self, prog: Program) -> bool:
+        return [(id(p), a, off, n) for p, (a, off, n) in zip(prog.params, prog.param_arena)] == self.layout
+
+    def publish_step(self):
+        """Write the step counter into ``optimizer.state`` (kept lazily: one Python loop per epoch, not per step)."""
+        for p in self.params:
+            self.optimizer.state[p]["step"].fill_(float(self.step))
+
+
+class LossHandle:
+    """The loss of one fused step; ``item()`` waits for that step only."""
+
+    def __init__(self, owner: "FusedTrainStep", k: int):
+        self.owner, self.k = owner, k
+        self._v: Optional[float] = None
+
+    def item(self) -> float:
+        if self._v is None:
+            self._v = self.owner._read_loss(self.k)
+        return self._v
+
+    __float__ = item
+
+    def tensor(self) -> torch.Tensor:
+        return torch.tensor(self.item())
+
+
+class PackedBatch:
+    """A batch already laid out in the staging format (device or pinned host): one copy per step."""
+
+    def __init__(self, buf: torch.Tensor, B: int, key):
+        self.buf, self.B, self.key = buf, B, key
+
+
+class FusedTrainStep:
+    def __init__(self, model, optimizer, x: Dict[str, torch.Tensor], device: torch.device, flat: Optional[FlatArenas] = None,
+                 grad_sync=None, use_graph: bool = True):
+        N.lib()
+        self.model, self.optimizer, self.device = model, optimizer, device
+        cols = model._columns()
+        self.cols = cols
+        self.B = int(x[cols[0]].shape[0])
+        self.dts = {c: x[c].dtype for c in cols}
+        self.key = (self.B, tuple(self.dts.values()))
+        b = ProgramBuilder(self.B, True)
+        model._lower(b, self.dts)
+        prog = b.finish()
+        if prog.out_slot < 0:
+            raise RuntimeError("the model's program has no head output")
+        self.prog = prog
+        if flat is None:
+            flat = FlatArenas(prog, optimizer, device)
+            model._programs = {}            # cached runners hold the old parameter pointers
+        elif not flat.matches(prog):
+            raise RuntimeError("gradient-arena layout changed between programs of one model")
+        self.flat = flat
+        self.grad_sync = grad_sync
+        self.runner = CudaRunner(prog, device)
+
+        # ---- staging layout: [columns..., labels f32] ; scalars live in their own small ring
+        self.layout = {}
+        off = 0
+        for name in prog.inputs:
+            if name == "__grad_out__":
+                continue
+            dt = self.dts[name]
+            nbytes = self.B * torch.empty((), dtype=dt).element_size()
+            self.layout[name] = (off, nbytes, _NP[dt])
+            off = _align(off + nbytes)
+        self.y_off = off
+        off = _align(off + 4 * self.B)
+        self.stage_bytes = off
+        self.dev_stage = torch.zeros(off, dtype=torch.uint8, device=device)
+        self.host_stage = [torch.zeros(off, dtype=torch.uint8).pin_memory() for _ in range(NSTAGE)]
+        self.host_np = [t.numpy() for t in self.host_stage]
+        self.stage_ev = [torch.cuda.Event() for _ in range(NSTAGE)]
+        # per-step scalars: 8 floats of Adam hyper-parameters + 4 ints of control
+        self.SC = 48
+        self.dev_scal = torch.zeros(self.SC, dtype=torch.uint8, device=device)
+        self.host_scal = torch.zeros(RING * self.SC, dtype=torch.uint8).pin_memory()
+        self.host_scal_np = self.host_scal.numpy()
+        self.loss_ring_dev = torch.zeros(RING, dtype=torch.float32, device=device)
+        self.loss_ring_host = torch.zeros(RING, dtype=torch.float32).pin_memory()
+        self.done_ev = [torch.cuda.Event() for _ in range(RING)]
+        self.gout = torch.zeros(self.B, dtype=torch.float32, device=device)
+        self.k = 0
+        self._launched = [-1] * RING
+
+        # ---- slot table: the program's slots + trainer extras
+        ns = len(prog.slot_desc)
+        X = {"label": ns, "loss": ns + 1, "ctrl": ns + 2, "hyper": ns + 3}
+        nxt = ns + 4
+        self.arena_slots = {}
+        for a in flat.size:
+            self.arena_slots[a] = (nxt, nxt + 1, nxt + 2, nxt + 3)       # p, g, m, v
+            nxt += 4
+        ptrs = np.zeros(nxt, dtype=np.uint64)
+        ptrs[:ns] = self.runner.ptrs
+        base = self.dev_stage.data_ptr()
+        for name, slot in prog.inputs.items():
+            if name == "__grad_out__":
+                ptrs[slot] = self.gout.data_ptr()
+            else:
+                ptrs[slot] = base + self.layout[name][0]
+        for i, d in enumerate(prog.slot_desc):
+            if d[0] == "grad":
+                ptrs[i] = flat.g[d[1]].data_ptr() + 4 * d[2]
+        ptrs[X["label"]] = base + self.y_off
+        ptrs[X["loss"]] = self.loss_ring_dev.data_ptr()
+        ptrs[X["hyper"]] = self.dev_scal.data_ptr()
+        ptrs[X["ctrl"]] = self.dev_scal.data_ptr() + 32
+        for a, (sp, sg, sm, sv) in self.arena_slots.items():
+            ptrs[sp], ptrs[sg], ptrs[sm], ptrs[sv] = (flat.p[a].data_ptr(), flat.g[a].data_ptr(), flat.m[a].data_ptr(),
+                                                      flat.v[a].data_ptr())
+        self.ptrs = ptrs
+
+        # ---- record lists
+        def rec(kind, ints=(), slots=()):
+            r = np.zeros((), dtype=N.REC_DTYPE)
+            r["kind"] = kind
+            r["s"][:] = -1
+            for i, v in enumerate(ints):
+                r["i"][i] = v
+            for i, v in enumerate(slots):
+                r["s"][i] = v
+            return r
+
+        split = ProgramBuilder._split64
+        bce = rec(N.OP_BCE, [self.B, N.DT_F32, RING], [prog.out_slot, X["label"], prog.gout_slot, X["loss"], X["ctrl"]])
+        zeros = [rec(N.OP_ZERO, split(4 * flat.size[a]), [self.arena_slots[a][1]]) for a in flat.size]
+        adams = [rec(N.OP_ADAM, [*split(flat.size[a]), 0], [*self.arena_slots[a], X["hyper"]]) for a in flat.size]
+        stack = lambda lst: np.stack(lst).astype(N.REC_DTYPE)      # noqa: E731
+        self.recs_a = np.concatenate([prog.recs_fwd, stack([bce] + zeros), prog.recs_bwd])
+        self.recs_b = stack(adams)
+        if grad_sync is None:
+            self.recs_a, self.recs_b = np.concatenate([self.recs_a, self.recs_b]), None
+        self.n_launch = (sum(1 for r in self.recs_a if int(r["kind"]) != N.OP_GROUP) +
+                         (0 if self.recs_b is None else len(self.recs_b)))
+        self.graph = None
+        self.use_graph = use_graph
+        self._warm = 0
+
+    # ---- device work of one step (graph-capturable: no syncs, no allocations) ------------------------
+    def _body(self):
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        N.program_run(self.recs_a, self.ptrs, stream)
+        if self.recs_b is not None:
+            self.grad_sync(self.flat.g)
+            N.program_run(self.recs_b, self.ptrs, stream)
+        N.memcpy_async(self.loss_ring_host.data_ptr(), self.loss_ring_dev.data_ptr(), 4 * RING, stream)
+
+    def _launch(self):
+        if self.use_graph and self.graph is None and self._warm >= 2:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.graph(g, stream=self._side_stream()):
+                self._body()
+            self.graph = g
+            torch.cuda.synchronize(self.device)
+            # the capture did not execute: fall through and replay it for this step
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._body()
+            self._warm += 1
+
+    def _side_stream(self):
+        if not hasattr(self, "_ss"):
+            self._ss = torch.cuda.Stream(self.device)
+        return self._ss
+
+    # ---- host side -------------------------------------------------------------------------------------
+    def pack(self, x: Dict[str, torch.Tensor], y: torch.Tensor, device=None) -> PackedBatch:
+        """Lay a batch out in the staging format once (bench / data pipeline); ``device`` = target of the buffer."""
+        buf = torch.zeros(self.stage_bytes, dtype=torch.uint8)
+        self._pack_into(buf.numpy(), x, y)
+        buf = buf.to(device) if device is not None and torch.device(device).type == "cuda" else buf.pin_memory()
+        return PackedBatch(buf, self.B, self.key)
+
+    def _pack_into(self, dst: np.ndarray, x, y):
+        for name, (off, nbytes, npdt) in self.layout.items():
+            t = x[name]
+            if t.dtype != self.dts[name] or t.shape[0] != self.B:
+                raise ValueError(f"column {name!r}: dtype/shape changed ({t.dtype}, {tuple(t.shape)})")
+            dst[off:off + nbytes].view(npdt)[:] = t.numpy()
+        dst[self.y_off:self.y_off + 4 * self.B].view(np.float32)[:] = y.numpy()
+
+    def _scalars(self):
+        g = self.optimizer.param_groups[0]
+        b1, b2 = g["betas"]
+        self.flat.step += 1
+        t = self.flat.step
+        bc1, bc2 = 1.0 - b1 ** t, 1.0 - b2 ** t
+        slot = self.k % RING
+        o = slot * self.SC
+        self.host_scal_np[o:o + 32].view(np.float32)[:6] = (g["lr"] / bc1, b1, b2, g["eps"], g["weight_decay"], 1.0 / math.sqrt(bc2))
+        self.host_scal_np[o + 32:o + 48].view(np.int32)[0] = slot
+        return o
+
+    def step(self, x, y=None) -> LossHandle:
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        slot = self.k % RING
+        if self._launched[slot] >= 0:
+            self.done_ev[slot].synchronize()            # ring entry (scalars + loss) of step k - RING is free again
+        if isinstance(x, PackedBatch):
+            if x.key != self.key:
+                raise ValueError("packed batch belongs to another program")
+            N.memcpy_async(self.dev_stage.data_ptr(), x.buf.data_ptr(), self.stage_bytes, stream)
+        else:
+            first = x[self.cols[0]]
+            if first.device.type == "cuda":
+                base = self.dev_stage.data_ptr()
+                for name, (off, nbytes, _dt) in self.layout.items():
+                    t = x[name].contiguous()
+                    N.memcpy_async(base + off, t.data_ptr(), nbytes, stream)
+                yy = y.float().contiguous()
+                N.memcpy_async(base + self.y_off, yy.data_ptr(), 4 * self.B, stream)
+                self._keep = (x, yy)
+            else:
+                i = self.k % NSTAGE
+                self.stage_ev[i].synchronize()
+                self._pack_into(self.host_np[i], x, y.float() if y.dtype != torch.float32 else y)
+                N.memcpy_async(self.dev_stage.data_ptr(), self.host_stage[i].data_ptr(), self.stage_bytes, stream)
+                self.stage_ev[i].record()
+        o = self._scalars()
+        N.memcpy_async(self.dev_scal.data_ptr(), self.host_scal.data_ptr() + o, self.SC, stream)
+        self._launch()
+        self.done_ev[slot].record()
+        self._launched[slot] = self.k
+        h = LossHandle(self, self.k)
+        self.k += 1
+        return h
+
+    def _read_loss(self, k: int) -> float:
+        slot = k % RING
+        if self._launched[slot] != k:
+            raise RuntimeError("loss handle expired: more than %d steps were launched since" % RING)
+        self.done_ev[slot].synchronize()
+        self.runner.check_indices()
+        return float(self.loss_ring_host[slot])

@@ -64,8 +64,12 @@ def randomise(model, seed):
         for name, p in model.named_parameters():
             if "embed_dict" in name:
                 p.copy_(torch.randn(p.shape, generator=g) * 0.5)
+            elif name.endswith("deep_weights"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.5 + 0.3)
             elif p.dim() == 1:
                 p.add_(torch.randn(p.shape, generator=g) * 0.1)
+            elif name.startswith(("u.", "v.")):      # HAMUR u/v are all-ones; keep the adapter scale sane
+                p.copy_(torch.randn(p.shape, generator=g) * 0.3)
         for name, b in model.named_buffers():
             if name.endswith("running_mean"):
                 b.copy_(torch.randn(b.shape, generator=g) * 0.1)

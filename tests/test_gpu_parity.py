@@ -72,10 +72,13 @@ def test_every_buffer_matches_interpreter(name, training):
     torch.cuda.synchronize()
     fails = gpu_util.compare_slots(rc, rr, [".dz", ".dstats"], atol=1e-5, rtol=2e-4)
     assert not fails, f"backward buffers differ: {fails[:5]}"
+    gmax = max(float(b.abs().max()) for b in gr)
     for p, a, b in zip(rc.prog.params, gc, gr):
         scale = max(float(b.abs().max()), 1e-3)
         err = float((a.cpu() - b).abs().max())
-        assert err <= 2e-4 * scale + 1e-6, f"param grad {tuple(p.shape)} err {err} scale {scale}"
+        # a bias feeding a norm has an analytically zero gradient (sum of cancelling terms): absolute floor
+        # relative to the largest gradient of the model
+        assert err <= 2e-4 * scale + 1e-5 * gmax + 1e-6, f"param grad {tuple(p.shape)} err {err} scale {scale}"
 
 
 def _prog(model, x):
@@ -91,41 +94,63 @@ def _prog(model, x):
 # --------------------------------------------------------------------------------------------
 import workloads
 
-BASELINE_CASES = {k: v for k, v in workloads.CASES.items() if k.startswith(("cfg1", "cfg2", "cfg3"))}
+BASELINE_CASES = dict(workloads.CASES)
+
+
+def _oracle(model_name, cfg, x, y, state, dt):
+    st = {}
+    for k, v in state.items():
+        v = v.clone()
+        if v.dtype.is_floating_point:
+            v = v.to(dt)
+            if "running_" not in k:
+                v.requires_grad_(True)
+        st[k] = v
+    xx = {k: (v.to(dt) if v.dtype.is_floating_point else v) for k, v in x.items()}
+    bn_out = {}
+    out = ref_models.forward(model_name, xx, st, cfg, training=True, bn_out=bn_out)
+    ref_models.bce_loss(out, y.to(dt)).backward()
+    return out.detach(), {k: v.grad for k, v in st.items() if v.requires_grad}, bn_out
 
 
 @pytest.mark.parametrize("case", sorted(BASELINE_CASES))
 def test_baseline_shapes_vs_oracle(case):
+    """BASELINE.json shapes.  Outputs: <= 1e-4 abs against the fp32 CPU oracle (north_star).  Gradients: judged
+    against the oracle evaluated in float64, with the fp32 CPU oracle's own distance to it as the noise floor --
+    deep BatchNorm stacks amplify fp32 rounding (STAR cfg4a: the CPU reference itself is 1e-2 of max|g| away from
+    float64), and a ReLU whose pre-activation lands within an ulp of 0 flips its derivative for one row (measure
+    zero, seen once in 16384 rows on M3oE), which a max-norm alone cannot tell from a bug; such a tensor must
+    still agree in the relative L2 norm with a vanishing fraction of outlier elements."""
     model_name, cfg, B = BASELINE_CASES[case]
-    if not model_factory.supported(model_name):
-        pytest.skip(f"{model_name} not lowered yet")
     torch.manual_seed(7)
     model = model_factory.build(model_name, cfg)
     gpu_util.randomise(model, 11)
     state = {k: v.clone() for k, v in model.state_dict().items()}
-    x, y = gpu_util.make_batch(cfg["features"], B, cfg["domain_num"], seed=5, zipf=True)
-    # oracle on the host
-    st = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running_" not in k else v.clone())
-          for k, v in state.items()}
-    bn_out = {}
-    ref = ref_models.forward(model_name, x, st, cfg, training=True, bn_out=bn_out)
-    ref_models.bce_loss(ref, y).backward()
+    x, y = gpu_util.make_batch(workloads.all_feature_specs(cfg), B, cfg["domain_num"], seed=5, zipf=True)
+    ref, g32, bn_out = _oracle(model_name, cfg, x, y, state, torch.float32)
+    _r64, g64, _ = _oracle(model_name, cfg, x, y, state, torch.float64)
     # CUDA path
     model.to(DEV).train()
     out = model({k: v.to(DEV) for k, v in x.items()})
     torch.nn.BCELoss()(out, y.to(DEV)).backward()
-    err = float((out.detach().cpu() - ref.detach()).abs().max())
+    err = float((out.detach().cpu() - ref).abs().max())
     assert err <= 1e-4, f"output err {err}"
-    worst = ("", 0.0)
     for k, p in model.named_parameters():
-        r = st[k].grad
-        assert (r is None) == (p.grad is None), k
-        if r is None:
+        t = g64[k]
+        assert (t is None) == (p.grad is None), k
+        if t is None:
             continue
-        scale = max(float(r.abs().max()), 1e-3 * float(max(abs(float(ref_models.bce_loss(ref, y).detach())), 1.0)))
-        e = float((p.grad.cpu() - r).abs().max()) / scale
-        worst = max(worst, (k, e), key=lambda t: t[1])
-    assert worst[1] <= 5e-4, f"gradient {worst}"
+        ours = p.grad.cpu().double()
+        scale = max(float(t.abs().max()), 1e-3)
+        e_ours = float((ours - t).abs().max()) / scale
+        e_ref = float((g32[k].double() - t).abs().max()) / scale
+        if e_ours <= max(5e-4, 4 * e_ref):
+            continue
+        nrm = max(float(t.norm()), 1e-12)
+        l2_ours, l2_ref = float((ours - t).norm()) / nrm, float((g32[k].double() - t).norm()) / nrm
+        outliers = float(((ours - t).abs() > 5e-4 * scale).double().mean())
+        assert l2_ours <= max(2e-3, 4 * l2_ref) and outliers <= 1e-4, \
+            f"gradient {k}: max-err {e_ours:.2e} (cpu fp32 noise {e_ref:.2e}), rel-L2 {l2_ours:.2e} (noise {l2_ref:.2e}), outliers {outliers:.2e}"
     sd = model.state_dict()
     for k, v in bn_out.items():
         torch.testing.assert_close(sd[k].cpu().to(v.dtype), v, atol=2e-5, rtol=1e-4)

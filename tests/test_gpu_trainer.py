@@ -1,0 +1,147 @@
+"""-m gpu: the fused training step (one CUDA graph: forward, BCELoss, backward, Adam) against
+(a) the reference loop run with the same CUDA model + torch.optim.Adam, (b) the CPU oracle + torch Adam."""
+import copy
+
+import pytest
+import torch
+
+from golden_util import Golden, golden_names
+import model_factory
+from oracle import ref_models
+from scenario_wise_rec_b200.trainers import CTRTrainer
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _batches(g, n):
+    out = []
+    for i in range(n):
+        gen = torch.Generator().manual_seed(100 + i)
+        x = {}
+        for k, v in g.x.items():
+            perm = torch.randperm(v.shape[0], generator=gen)
+            x[k] = v[perm].clone()
+        y = (torch.rand(g.B, generator=gen) < 0.4).float()
+        out.append((x, y))
+    return out
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_fused_step_matches_reference_loop(name):
+    g = Golden(name)
+    steps = 5
+    batches = _batches(g, steps)
+    trainers = []
+    for fused in (True, False):
+        m = model_factory.build(g.model, g.cfg)
+        m.load_state_dict(g.state0)
+        t = CTRTrainer(m, "golden", optimizer_params={"lr": 1e-2, "weight_decay": 1e-4}, device=DEV, fused=fused)
+        m.train()
+        trainers.append(t)
+    losses = [[], []]
+    for x, y in batches:
+        for i, t in enumerate(trainers):
+            losses[i].append(float(t.train_step(x, y).item()))
+    assert trainers[0]._steps, "the fused path was not taken"
+    assert trainers[0]._steps[next(iter(trainers[0]._steps))].graph is not None, "the step was not captured in a CUDA graph"
+    assert not trainers[1]._steps
+    for a, b in zip(*losses):
+        assert abs(a - b) <= 2e-5 * max(1.0, abs(b)), (losses[0], losses[1])
+    sa, sb = trainers[0].model.state_dict(), trainers[1].model.state_dict()
+    for k in sb:
+        torch.testing.assert_close(sa[k].float(), sb[k].float(), atol=2e-5, rtol=2e-4, msg=lambda m, k=k: f"{k}: {m}")
+    # optimizer state: same keys, same moments, same step counter
+    oa, ob = trainers[0].optimizer.state_dict(), trainers[1].optimizer.state_dict()
+    assert oa["param_groups"][0]["params"] == ob["param_groups"][0]["params"]
+    assert set(oa["state"]) == set(ob["state"])
+    for pid, st in ob["state"].items():
+        assert float(oa["state"][pid]["step"]) == float(st["step"]) == steps
+        torch.testing.assert_close(oa["state"][pid]["exp_avg"], st["exp_avg"], atol=1e-6, rtol=2e-3)
+        torch.testing.assert_close(oa["state"][pid]["exp_avg_sq"], st["exp_avg_sq"], atol=1e-9, rtol=2e-3)
+    # parameters the reference never reaches keep grad None and are not moved by Adam
+    for k, p in trainers[0].model.named_parameters():
+        if k in g.grad_none:
+            assert p.grad is None and torch.equal(p.detach().cpu(), g.state0[k]), k
+
+
+def test_fused_step_matches_cpu_oracle():
+    g = Golden("mmoe_small")
+    steps = 4
+    batches = _batches(g, steps)
+    m = model_factory.build(g.model, g.cfg)
+    m.load_state_dict(g.state0)
+    t = CTRTrainer(m, "golden", optimizer_params={"lr": 1e-2, "weight_decay": 1e-4}, device=DEV)
+    m.train()
+    st = g.leaf_state()
+    params = [v for v in st.values() if v.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-2, weight_decay=1e-4)
+    for x, y in batches:
+        loss = t.train_step(x, y).item()
+        bn_out = {}
+        out = ref_models.forward(g.model, x, st, g.cfg, training=True, bn_out=bn_out)
+        ref_loss = ref_models.bce_loss(out, y)
+        for p in params:
+            p.grad = None
+        ref_loss.backward()
+        opt.step()
+        st.update(bn_out)
+        assert abs(loss - float(ref_loss)) <= 2e-5
+    sd = m.state_dict()
+    for k, v in st.items():
+        torch.testing.assert_close(sd[k].cpu().to(v.dtype), v.detach(), atol=2e-5, rtol=2e-4, msg=lambda mm, k=k: f"{k}: {mm}")
+
+
+def test_train_one_epoch_and_eval_api():
+    g = Golden("sharedbottom_small")
+    m = model_factory.build(g.model, g.cfg)
+    m.load_state_dict(g.state0)
+    t = CTRTrainer(m, "golden", device=DEV, n_epoch=1)
+    loader = _batches(g, 23)
+    w0 = copy.deepcopy(m.state_dict())
+    t.train_one_epoch(loader)
+    assert any(not torch.equal(w0[k].cpu(), v.cpu()) for k, v in m.state_dict().items())
+    auc, ll = t.evaluate(m, loader)
+    assert 0.0 <= auc <= 1.0 and ll > 0
+    dl, da, tl, ta = t.evaluate_multi_domain_loss(m, loader, g.cfg["domain_num"])
+    assert len(dl) == len(da) == g.cfg["domain_num"] and abs(tl - ll) < 1e-9
+    preds = t.predict(m, loader)
+    assert len(preds) == 23 * g.B
+    # a different batch size (last partial batch of an epoch) builds a second program on the same flat arenas
+    x, y = loader[0]
+    m.train()
+    t.train_step({k: v[:17] for k, v in x.items()}, y[:17]).item()
+    assert len(t._steps) == 2
+
+
+def test_out_of_range_index_raises_from_fused_step():
+    g = Golden("sharedbottom_small")
+    m = model_factory.build(g.model, g.cfg)
+    m.load_state_dict(g.state0)
+    t = CTRTrainer(m, "golden", device=DEV)
+    m.train()
+    x, y = _batches(g, 1)[0]
+    x["s1"][5] = 7           # vocab of s1 is 7
+    with pytest.raises(IndexError):
+        t.train_step(x, y).item()
+
+
+def test_packed_batches_device_and_host():
+    g = Golden("mmoe_small")
+    batches = _batches(g, 6)
+    res = []
+    for mode in ("dict", "packed_host", "packed_dev"):
+        m = model_factory.build(g.model, g.cfg)
+        m.load_state_dict(g.state0)
+        t = CTRTrainer(m, "golden", device=DEV)
+        m.train()
+        pk = t.packer(batches[0][0])
+        for x, y in batches:
+            if mode == "dict":
+                t.train_step(x, y)
+            else:
+                t.train_step(pk.pack(x, y, device=DEV if mode == "packed_dev" else None))
+        torch.cuda.synchronize()
+        res.append({k: v.clone().cpu() for k, v in m.state_dict().items()})
+    for k in res[0]:
+        assert torch.equal(res[0][k], res[1][k]) and torch.equal(res[0][k], res[2][k]), k
