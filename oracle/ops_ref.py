@@ -282,14 +282,18 @@ class RefRunner:
                 Y.stats[:, 0] += y.double().sum(0)
                 Y.stats[:, 1] += (y.double() ** 2).sum(0)
 
-    def _op_6(self, h, subs):       # FC_DGRAD (fan-in)
-        dA = None
+    def _op_6(self, h, subs):       # FC_DGRAD (fan-in per destination; i[12] = destination index)
+        by_dst = {}
         for r in subs:
-            Y = _Act(self, r, 12, 4, 2)
-            t = Y.dy() @ self._weff(r)
-            dA = t if dA is None else dA + t
-        D = _Act(self, subs[0], 0, 0, 0)
-        D.write_grad(dA[:, :D.n], accumulate=bool(int(subs[0]["i"][11]) & 2))    # D.n < K: detached trailing columns
+            by_dst.setdefault(int(r["i"][12]), []).append(r)
+        for recs in by_dst.values():
+            dA = None
+            for r in recs:
+                Y = _Act(self, r, 12, 4, 2)
+                t = Y.dy() @ self._weff(r)
+                dA = t if dA is None else dA + t
+            D = _Act(self, recs[0], 0, 0, 0)
+            D.write_grad(dA[:, :D.n], accumulate=bool(int(recs[0]["i"][11]) & 2))    # D.n < K: detached trailing columns
 
     def _op_7(self, h, subs):       # FC_WGRAD
         for r in subs:

@@ -82,18 +82,30 @@ static FcGroup decode_fc(const swr_rec_t& r, Ctx& c) {
 
 static int run_fc(int kind, const swr_rec_t* subs, int n, int64_t B, Ctx& c, cudaStream_t st) {
   std::vector<FcGroup> groups(n);
-  for (int i = 0; i < n; ++i) groups[i] = decode_fc(subs[i], c);
+  std::vector<int> dst(n);
+  for (int i = 0; i < n; ++i) { groups[i] = decode_fc(subs[i], c); dst[i] = subs[i].i[12]; }
   if (!c.ok) return SWR_ERR_INVALID;
+  if (kind == SWR_OP_FC_DGRAD) {
+    // several destinations per launch (i[12] = destination index, groups sorted by it); chunk at destination
+    // boundaries when the group budget of one launch is exceeded, inside a destination only as a last resort
+    int o = 0;
+    while (o < n) {
+      int m = n - o < kMaxGroups ? n - o : kMaxGroups;
+      if (o + m < n) {
+        int cut = m;
+        while (cut > 0 && dst[o + cut] == dst[o + cut - 1]) --cut;
+        if (cut > 0) m = cut;
+      }
+      if (o > 0 && dst[o] == dst[o - 1]) for (int i = 0; i < m && dst[o + i] == dst[o]; ++i) groups[o + i].flags |= FC_A_ACCUMULATE;
+      int rc = launch_fc_dgrad(groups.data() + o, dst.data() + o, m, B, st);
+      if (rc) return rc;
+      o += m;
+    }
+    return SWR_OK;
+  }
   for (int o = 0; o < n; o += kMaxGroups) {
     const int m = n - o < kMaxGroups ? n - o : kMaxGroups;
-    int rc;
-    if (kind == SWR_OP_FC_FWD) rc = launch_fc_fwd(groups.data() + o, m, B, st);
-    else if (kind == SWR_OP_FC_WGRAD) rc = launch_fc_wgrad(groups.data() + o, m, B, st);
-    else {
-      // fan-in chunks after the first accumulate into the destination
-      if (o > 0) for (int i = 0; i < m; ++i) groups[o + i].flags |= FC_A_ACCUMULATE;
-      rc = launch_fc_dgrad(groups.data() + o, m, B, st);
-    }
+    int rc = (kind == SWR_OP_FC_FWD) ? launch_fc_fwd(groups.data() + o, m, B, st) : launch_fc_wgrad(groups.data() + o, m, B, st);
     if (rc) return rc;
   }
   return SWR_OK;

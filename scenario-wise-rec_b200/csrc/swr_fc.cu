@@ -38,6 +38,11 @@ struct FcParams {
   float inv_count;
   int splits;          // wgrad: number of batch splits
   int rows_per_split;  // wgrad
+  // dgrad: several destinations per launch; destination d owns groups [dst_group[d], dst_group[d+1]) (its fan-in)
+  // and CTA tiles [dst_tile[d], dst_tile[d+1])
+  int n_dst;
+  int dst_group[kMaxGroups + 1];
+  int dst_tile[kMaxGroups + 1];
 };
 
 __device__ __forceinline__ bool is_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -285,18 +290,23 @@ __global__ void __launch_bounds__(256) fc_dgrad_kernel(const __grid_constant__ F
   extern __shared__ __align__(16) float smem[];
   float* As = smem;
   float* Bs = As + BK * C::LDA;
-  float* dc = Bs + BK * C::LDB;   // [3][Kc]: c0, c1, c2 over the concatenated (BK-padded) group columns
+  float* dc = Bs + BK * C::LDB;   // [3][Kc]: c0, c1, c2 over the concatenated (BK-padded) group columns of this destination
   const int tid = threadIdx.x, tx = tid % C::TX, ty = tid / C::TX;
-  const ActDev& D = p.g[0].A;     // destination activation (shared by all groups)
+  int d = 0;
+  while (d + 1 < p.n_dst && p.dst_tile[d + 1] <= (int)blockIdx.x) ++d;
+  const int gs = p.dst_group[d], ge = p.dst_group[d + 1];
+  const ActDev& D = p.g[gs].A;    // destination activation (shared by the groups of this fan-in)
   const int M = p.B, Kd = D.n;
   const int nt_n = (Kd + C::BN - 1) / C::BN;
-  const int m0 = (blockIdx.x / nt_n) * C::BM, j0 = (blockIdx.x % nt_n) * C::BN;
-  const int nk = p.tile_start[p.n_groups];
+  const int local = blockIdx.x - p.dst_tile[d];
+  const int m0 = (local / nt_n) * C::BM, j0 = (local % nt_n) * C::BN;
+  const int kt0 = p.tile_start[gs];
+  const int nk = p.tile_start[ge] - kt0;
   const int Kc = nk * BK;
 
-  for (int g = 0; g < p.n_groups; ++g) {
+  for (int g = gs; g < ge; ++g) {
     const FcGroup& G = p.g[g];
-    const int base = p.tile_start[g] * BK, span = (p.tile_start[g + 1] - p.tile_start[g]) * BK;
+    const int base = (p.tile_start[g] - kt0) * BK, span = (p.tile_start[g + 1] - p.tile_start[g]) * BK;
     for (int n = tid; n < span; n += C::NT) {
       DyCoef c = {0.f, 0.f, 0.f};
       if (n < G.Y.n) c = dy_coef(G.Y, n, p.inv_count);
@@ -306,14 +316,14 @@ __global__ void __launch_bounds__(256) fc_dgrad_kernel(const __grid_constant__ F
   __syncthreads();
 
   float4 ra[C::A_IT], rb[C::B_IT];
-  int cur_g = 0;
+  int cur_g = gs;
   bool kn = false;
-  auto loadAB = [&](int kt) {
-    while (cur_g + 1 < p.n_groups && p.tile_start[cur_g + 1] <= kt) ++cur_g;
+  auto loadAB = [&](int kt) {     // kt: k-tile index inside this destination's fan-in
+    while (cur_g + 1 < ge && p.tile_start[cur_g + 1] - kt0 <= kt) ++cur_g;
     const FcGroup& G = p.g[cur_g];
     const int N = G.Y.n;
-    const int nl0 = (kt - p.tile_start[cur_g]) * BK;   // first column of this k-tile inside the group
-    const int cb = kt * BK;                            // same position in the coefficient arrays
+    const int nl0 = (kt - (p.tile_start[cur_g] - kt0)) * BK;   // first column of this k-tile inside the group
+    const int cb = kt * BK;                                    // same position in the coefficient arrays
     const bool vecY = is_al16(G.Y.dz) && is_al16(G.Y.raw) && (G.Y.ld % 4 == 0);
     const bool vecW = is_al16(G.W) && (G.ldw % 4 == 0) && (!G.W2 || is_al16(G.W2));
     const bool need_raw = (G.Y.norm.mode == SWR_NORM_BATCH);
@@ -378,7 +388,7 @@ __global__ void __launch_bounds__(256) fc_dgrad_kernel(const __grid_constant__ F
   }
 
   // epilogue: backward through the destination's activation / norm (stage 1), store dz
-  const bool accumulate = (p.g[0].flags & FC_A_ACCUMULATE) != 0;
+  const bool accumulate = (p.g[gs].flags & FC_A_ACCUMULATE) != 0;
   const bool has_norm = D.norm.mode != SWR_NORM_NONE;
   const bool plainD = !has_norm && D.act == SWR_ACT_NONE;
   double s1[C::TN], s2[C::TN];
@@ -614,8 +624,14 @@ static int run_dgrad(FcParams& p, cudaStream_t st) {
   int kt = 0;
   for (int g = 0; g < p.n_groups; ++g) { p.tile_start[g] = kt; kt += ceil_div(p.g[g].Y.n, BK); }
   p.tile_start[p.n_groups] = kt;
-  const int tiles = ceil_div(p.B, C::BM) * ceil_div(p.g[0].A.n, C::BN);
-  const size_t sm = sizeof(float) * (C::SMEM_TILE + 3 * (size_t)kt * BK);
+  int tiles = 0, kmax = 0;
+  for (int d = 0; d < p.n_dst; ++d) {
+    p.dst_tile[d] = tiles;
+    tiles += ceil_div(p.B, C::BM) * ceil_div(p.g[p.dst_group[d]].A.n, C::BN);
+    kmax = max(kmax, p.tile_start[p.dst_group[d + 1]] - p.tile_start[p.dst_group[d]]);
+  }
+  p.dst_tile[p.n_dst] = tiles;
+  const size_t sm = sizeof(float) * (C::SMEM_TILE + 3 * (size_t)kmax * BK);
   const size_t need = max(sm, sizeof(double) * 16 * C::BN);
   int rc = set_smem(fc_dgrad_kernel<C>, need);
   if (rc) return rc;
@@ -624,23 +640,31 @@ static int run_dgrad(FcParams& p, cudaStream_t st) {
   return SWR_OK;
 }
 
-int launch_fc_dgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st) {
+// groups must be sorted by destination: dst_of[g] is non-decreasing, groups of one destination share A
+int launch_fc_dgrad(const FcGroup* groups, const int* dst_of, int n_groups, int64_t B, cudaStream_t st) {
   if (B <= 0) return SWR_OK;
   int rc = check_groups(groups, n_groups, "fc_dgrad");
   if (rc) return rc;
   FcParams p{};
+  int n_dst = 0, kd_max = 0;
+  int64_t tiles128 = 0;
   for (int g = 0; g < n_groups; ++g) {
     p.g[g] = groups[g];
-    if (groups[g].A.raw != groups[0].A.raw || groups[g].A.n != groups[0].A.n) { set_error("fc_dgrad: groups must share their input activation"); return SWR_ERR_INVALID; }
+    if (g == 0 || dst_of[g] != dst_of[g - 1]) {
+      if (g > 0 && dst_of[g] < dst_of[g - 1]) { set_error("fc_dgrad: groups are not sorted by destination"); return SWR_ERR_INVALID; }
+      p.dst_group[n_dst++] = g;
+      if (!groups[g].A.dz) { set_error("fc_dgrad: destination has no gradient buffer"); return SWR_ERR_INVALID; }
+      kd_max = max(kd_max, groups[g].A.n);
+      tiles128 += (int64_t)ceil_div(B, 128) * ((groups[g].A.n + 63) / 64);
+    } else if (groups[g].A.raw != groups[g - 1].A.raw || groups[g].A.n != groups[g - 1].A.n) {
+      set_error("fc_dgrad: groups of one destination must share their input activation"); return SWR_ERR_INVALID;
+    }
     if (!groups[g].Y.dz) { set_error("fc_dgrad: group %d has no output gradient buffer", g); return SWR_ERR_INVALID; }
   }
-  if (!groups[0].A.dz) { set_error("fc_dgrad: destination has no gradient buffer"); return SWR_ERR_INVALID; }
+  p.dst_group[n_dst] = n_groups;
+  p.n_dst = n_dst;
   p.n_groups = n_groups; p.B = (int)B; p.inv_count = 1.0f / (float)B;
-  const int Kd = groups[0].A.n;
-  if (Kd > 16) {
-    const int64_t tiles128 = (int64_t)ceil_div(B, 128) * ((Kd + 63) / 64);
-    return tiles128 >= 296 ? run_dgrad<CfgWide>(p, st) : run_dgrad<CfgMid>(p, st);
-  }
+  if (kd_max > 16) return tiles128 >= 296 ? run_dgrad<CfgWide>(p, st) : run_dgrad<CfgMid>(p, st);
   return run_dgrad<CfgNarrowS>(p, st);
 }
 

@@ -40,7 +40,7 @@ struct FcGroup {
 enum { FC_A_NEEDS_GRAD = 1, FC_A_ACCUMULATE = 2 };
 
 int launch_fc_fwd(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st);
-int launch_fc_dgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st);
+int launch_fc_dgrad(const FcGroup* groups, const int* dst_of, int n_groups, int64_t B, cudaStream_t st);
 int launch_fc_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st);
 
 // ---- row-local ops ----------------------------------------------------------------------

@@ -560,8 +560,8 @@ class ProgramBuilder:
                 for g in gs:
                     if g.src.needs_grad and not g.detach:
                         by_src.setdefault(id(g.src), []).append(g)
-                for lst in by_src.values():
-                    blk.append(("dgrad", lst))
+                if by_src:
+                    blk.append(("dgrad", list(by_src.values())))
                 bwd_blocks.append(blk)
             elif kind == "pool":
                 entries, experts, H = op[1], op[2], op[3]
@@ -704,15 +704,19 @@ class ProgramBuilder:
                     bwd.append(self._hdr(N.OP_FC_WGRAD, len(gs)))
                     bwd.extend(self._fc_rec(g) for g in gs)
                 elif tag == "dgrad":
-                    lst = item[1]
-                    src = lst[0].src
-                    flags = 1 | (0 if first_write(src) else 2)
-                    bwd.append(self._hdr(N.OP_FC_DGRAD, len(lst)))
-                    for g in lst:
-                        r = self._fc_rec(g, flags)
-                        if src.grad_cols is not None:
-                            r["i"][1] = src.grad_cols        # narrower destination: only these columns get dA
-                        bwd.append(r)
+                    # ONE launch for every destination of this level: groups sorted by destination (i[12]), each
+                    # destination sums its own fan-in
+                    lists = item[1]
+                    bwd.append(self._hdr(N.OP_FC_DGRAD, sum(len(lst) for lst in lists), i1=len(lists)))
+                    for di, lst in enumerate(lists):
+                        src = lst[0].src
+                        flags = 1 | (0 if first_write(src) else 2)
+                        for g in lst:
+                            r = self._fc_rec(g, flags)
+                            r["i"][12] = di
+                            if src.grad_cols is not None:
+                                r["i"][1] = src.grad_cols        # narrower destination: only these columns get dA
+                            bwd.append(r)
                 elif tag == "sumgrad":
                     _, src, views = item
                     live = [v for v in views if v.needs_grad]
