@@ -198,6 +198,8 @@ class RefRunner:
                 v = self._view(dz, ld, n)
                 v.zero_() if g is None else v.copy_(g)
         self._run(prog.recs_bwd)
+        if getattr(self, "grad_sync", None) is not None:      # data parallel: mirrors CudaRunner.backward
+            self.grad_sync(arenas)
         return [arenas[a][off:off + n].view(p.shape) for p, (a, off, n) in zip(prog.params, prog.param_arena)]
 
     # ---- interpreter ------------------------------------------------------------------------
@@ -609,3 +611,15 @@ class RefRunner:
         p.sub_(step_size * m / (v.sqrt() * ibc2 + eps))
         if int(h["i"][2]):
             g.zero_()
+
+
+# ---- CPU stand-ins for parallel.local_gather / local_scatter (K1 / K2 on one field), used by the gloo tests ----
+def ref_local_gather(table, idx, out):
+    ok = (idx >= 0) & (idx < table.shape[0])
+    out.zero_()
+    out[ok] = table[idx[ok]]
+
+
+def ref_local_scatter(grad_rows, idx, gtable):
+    ok = (idx >= 0) & (idx < gtable.shape[0])
+    gtable.index_add_(0, idx[ok], grad_rows[ok])

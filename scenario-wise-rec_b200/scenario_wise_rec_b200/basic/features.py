@@ -24,13 +24,15 @@ class SparseFeature(object):
         self.shared_with = shared_with
         self.padding_idx = padding_idx
         self.initializer = initializer
+        self.shard = None           # parallel.ShardInfo when the table is row-sharded across ranks (parallel.shard_features)
 
     def __repr__(self):
         return f"<SparseFeature {self.name} with Embedding shape ({self.vocab_size}, {self.embed_dim})>"
 
     def get_embedding_layer(self):
         if not hasattr(self, "embed"):
-            self.embed = self.initializer(self.vocab_size, self.embed_dim)
+            rows = self.vocab_size if self.shard is None else self.shard.local_rows(self.vocab_size)
+            self.embed = self.initializer(rows, self.embed_dim)
         return self.embed
 
 

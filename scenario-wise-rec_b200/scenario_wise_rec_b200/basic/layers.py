@@ -78,8 +78,22 @@ class EmbeddingLayer(FusedModule):
                 raise NotImplementedError(f"feature type {type(fea).__name__} is outside the accelerated path")
         return sparse, dense
 
-    def lower(self, b: ProgramBuilder, features, col_dtypes) -> Act:
+    def split_sharded(self, b: ProgramBuilder, features, col_dtypes):
+        """``split`` with row-sharded tables replaced by their virtual table / virtual index column (parallel.py)."""
         sparse, dense = self.split(features)
+        feas = [f for f in features if isinstance(f, SparseFeature)]
+        out = []
+        for (name, tab), fea in zip(sparse, feas):
+            if getattr(fea, "shard", None) is not None:
+                f = b.virtual_field(fea, tab)
+                col_dtypes[f.vcol] = torch.int64
+                out.append((f.vcol, f.virt))
+            else:
+                out.append((name, tab))
+        return out, dense
+
+    def lower(self, b: ProgramBuilder, features, col_dtypes) -> Act:
+        sparse, dense = self.split_sharded(b, features, col_dtypes)
         return b.gather(sparse, dense, col_dtypes)
 
     @staticmethod

@@ -77,6 +77,7 @@ class FusedModule(nn.Module):
         r = self._programs.get(key)
         if r is None:
             b = ProgramBuilder(B, self.training)
+            b.exchange = self._get_exchange()
             self._lower(b, dts)
             prog = b.finish()
             factory = type(self)._runner_factory
@@ -85,11 +86,37 @@ class FusedModule(nn.Module):
             self._programs[key] = r
         return r
 
+    def _get_exchange(self):
+        """The ShardedExchange of this model (created on first use; None when no table is row-sharded)."""
+        ex = self.__dict__.get("_exchange")
+        if ex is None and any(getattr(f, "shard", None) is not None for fl in self._all_feature_lists() for f in fl):
+            from .parallel import ShardedExchange
+            ex = self.__dict__["_exchange"] = ShardedExchange()
+        return ex
+
+    def _all_feature_lists(self):
+        if hasattr(self, "_feature_lists"):
+            return self._feature_lists()
+        return [getattr(self, "_active", None) or getattr(self, "features", [])]
+
     def _run(self, x):
         r = self._runner(x)
         prog: Program = r.prog
-        if torch.is_grad_enabled() and any(p.requires_grad for p in prog.params):
-            outs = _ProgramFn.apply(r, x, *prog.params)
+        want_grad = torch.is_grad_enabled() and any(p.requires_grad for p in prog.params)
+        params = prog.params
+        if prog.virtual_fields:
+            # row-sharded tables: exchange looked-up rows over NVLink, then read them through virtual tables
+            from .parallel import ShardedLookup
+            ex, x, subst = self._get_exchange(), dict(x), {}
+            for f in prog.virtual_fields:
+                if want_grad and f.shard.requires_grad:
+                    subst[id(f.virt)] = ShardedLookup.apply(f.shard, x[f.name], ex, f)
+                else:
+                    ex.lookup(f, x[f.name])
+                x[f.vcol] = f.vidx
+            params = [subst.get(id(p), p) for p in prog.params]
+        if want_grad:
+            outs = _ProgramFn.apply(r, x, *params)
         else:
             outs = r.forward(x)
         return outs[0] if len(outs) == 1 else outs
@@ -102,3 +129,5 @@ class FusedModule(nn.Module):
             torch.cuda.synchronize()
         for r in self._programs.values():
             r.check_indices()
+        if self.__dict__.get("_exchange") is not None:
+            self.__dict__["_exchange"].check_indices()

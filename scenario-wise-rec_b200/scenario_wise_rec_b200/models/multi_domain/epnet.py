@@ -35,8 +35,8 @@ class EPNet(MultiDomainModel):
         return cols[:-1]            # EPNet never reads domain_indicator
 
     def _lower(self, b, col_dtypes):
-        ss, sd = self.sce_embedding.split(self.sce_features)
-        ags, agd = self.agn_embedding.split(self.agn_features)
+        ss, sd = self.sce_embedding.split_sharded(b, self.sce_features, col_dtypes)
+        ags, agd = self.agn_embedding.split_sharded(b, self.agn_features, col_dtypes)
         x = b.gather_parts([(ss, sd, True), (ags, agd, True)], col_dtypes)
         x.grad_cols = self.sce_dims                      # the gate net sees agn_x.detach()
         agn = b.subview(x, self.sce_dims, self.agn_dims)

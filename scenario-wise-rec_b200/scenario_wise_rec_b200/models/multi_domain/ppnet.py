@@ -46,8 +46,8 @@ class PPNet(MultiDomainModel):
 
     def _lower(self, b, col_dtypes):
         D = self.domain_num
-        ids, idd = self.id_embedding.split(self.id_features)
-        ags, agd = self.agn_embedding.split(self.agn_features)
+        ids, idd = self.id_embedding.split_sharded(b, self.id_features, col_dtypes)
+        ags, agd = self.agn_embedding.split_sharded(b, self.agn_features, col_dtypes)
         x = b.gather_parts([(ids, idd, True), (ags, agd, False)], col_dtypes)
         x.grad_cols = self.id_dims
         L = len(self.domain_tower[0].mlp_layers)

@@ -98,6 +98,7 @@ class Program:
     oob_slot: int = -1
     outputs: List[Tuple[int, int, int, int]] = field(default_factory=list)   # plain [B, n] outputs: (raw slot, ld, n, dz slot)
     labels: Dict[int, str] = field(default_factory=dict)
+    virtual_fields: list = field(default_factory=list)   # parallel._Field of every row-sharded table the program reads
     n_launch_fwd: int = 0
     n_launch_bwd: int = 0
 
@@ -116,7 +117,9 @@ class ProgramBuilder:
         self.params: List[torch.nn.Parameter] = []
         self._param_slot: Dict[int, int] = {}
         self.param_arena: List[Tuple[str, int, int]] = []
-        self.arena_size = {"dense": 0, "emb": 0}
+        self.arena_size = {"dense": 0, "emb": 0, "virt": 0}
+        self.exchange = None                 # parallel.ShardedExchange of the owning model (row-sharded tables)
+        self.virtual_fields: list = []
         self.tape: List[tuple] = []
         self.norm_acts: List[Act] = []
         self.out_slot = self.gout_slot = self.oob_slot = -1
@@ -164,6 +167,15 @@ class ProgramBuilder:
             self.param_arena.append((arena, off, p.numel()))
             self._param_slot[key] = self._new_slot(("grad", arena, off, p.numel()))
         return self._param_slot[key]
+
+    def virtual_field(self, fea, shard_param):
+        """The virtual table of a row-sharded feature for this batch size (see parallel.py)."""
+        if self.exchange is None:
+            raise RuntimeError(f"feature {fea.name!r} is row-sharded but the model has no ShardedExchange")
+        f = self.exchange.field(fea, shard_param, self.B)
+        if f not in self.virtual_fields:
+            self.virtual_fields.append(f)
+        return f
 
     # ---- activations ------------------------------------------------------------------
     def new_act(self, n: int, norm: Optional[Norm] = None, act: int = N.ACT_NONE, raw: Optional[int] = None,
@@ -531,7 +543,8 @@ class ProgramBuilder:
                         subs.append(r)
                         if tab.requires_grad and diff:
                             g = r.copy()
-                            g["s"][0] = self.grad(tab, "emb")
+                            is_virt = any(tab is f.virt for f in self.virtual_fields)
+                            g["s"][0] = self.grad(tab, "virt" if is_virt else "emb")
                             srecs.append(g)
                         col += E
                     for name in dense:
@@ -802,7 +815,7 @@ class ProgramBuilder:
                        params=self.params, param_arena=self.param_arena, arena_size=dict(self.arena_size),
                        out_slot=self.out_slot, gout_slot=self.gout_slot, oob_slot=self.oob_slot,
                        outputs=[(a.raw, a.ld, a.n, a.dz if a.needs_grad else -1) for a in self._outputs],
-                       labels=dict(self.labels),
+                       labels=dict(self.labels), virtual_fields=list(self.virtual_fields),
                        n_launch_fwd=launches(fwd), n_launch_bwd=launches(bwd))
 
 
@@ -823,7 +836,7 @@ class CudaRunner:
         # out-of-range index flag: mapped pinned host memory, readable without a device sync
         self.oob = torch.zeros(2, dtype=torch.int32).pin_memory()
         self.ptrs = np.zeros(len(prog.slot_desc), dtype=np.uint64)
-        self._grad_slots = {"dense": ([], []), "emb": ([], [])}
+        self._grad_slots = {k: ([], []) for k in prog.arena_size}
         b32, b64 = self.ws32.data_ptr(), self.ws64.data_ptr()
         for i, d in enumerate(prog.slot_desc):
             if d[0] == "static":

@@ -66,8 +66,9 @@ class CTRTrainer(object):
         import torch.distributed as dist
 
         def sync(arenas):
-            for a in arenas.values():
-                if a.numel() > 1:
+            for name, a in arenas.items():
+                # "virt" / "shard": gradients of row-sharded tables are routed by the embedding exchange instead
+                if name in ("dense", "emb") and a.numel() > 1:
                     dist.all_reduce(a, op=dist.ReduceOp.AVG, group=group)
 
         self.model._grad_sync = sync
