@@ -45,21 +45,36 @@ def _align(n: int, a: int = 16) -> int:
 
 
 class FlatArenas:
-    """Flat parameter / gradient / Adam-moment storage shared by every program of one model."""
+    """Flat parameter / gradient / Adam-moment storage shared by every program of one model.
+
+    Arenas: ``dense`` (tower / expert / gate weights), ``emb`` (replicated tables), ``shard`` (this rank's rows of
+    row-sharded tables) hold parameters, gradients and both moments; ``virt`` holds only the gradients of the
+    virtual tables of the embedding exchange (parallel.py), which are per-step buffers, not parameters."""
 
     def __init__(self, prog: Program, optimizer, device):
         self.device = device
-        self.layout = [(id(p), a, off, n) for p, (a, off, n) in zip(prog.params, prog.param_arena)]
+        entries = [(p, a, off, n) for p, (a, off, n) in zip(prog.params, prog.param_arena)]
         self.size = {k: max(v, 4) for k, v in prog.arena_size.items()}
+        off = 0
+        self.shards = []
+        for f in prog.virtual_fields:
+            if f.shard.requires_grad and all(f.shard is not q for q, *_ in self.shards):
+                self.shards.append((f.shard, "shard", off, f.shard.numel()))
+                off += _align(f.shard.numel(), 4)
+        self.size["shard"] = max(off, 4)
+        self.layout = [(id(p), a, o, n) for p, a, o, n in entries]
         z = lambda k: torch.zeros(self.size[k], dtype=torch.float32, device=device)      # noqa: E731
-        self.p = {k: z(k) for k in self.size}
         self.g = {k: z(k) for k in self.size}
-        self.m = {k: z(k) for k in self.size}
-        self.v = {k: z(k) for k in self.size}
-        self.params = list(prog.params)
+        self.opt_arenas = [k for k in self.size if k != "virt"]
+        self.p = {k: z(k) for k in self.opt_arenas}
+        self.m = {k: z(k) for k in self.opt_arenas}
+        self.v = {k: z(k) for k in self.opt_arenas}
+        self.params = []
         step = 0
         with torch.no_grad():
-            for p, (a, off, n) in zip(prog.params, prog.param_arena):
+            for p, a, off, n in entries + self.shards:
+                if a == "virt":
+                    continue
                 if p.device != device or p.dtype != torch.float32:
                     raise RuntimeError("parameters must be float32 on the trainer's device")
                 flat = self.p[a][off:off + n]
@@ -73,16 +88,25 @@ class FlatArenas:
                     step = max(step, int(st["step"]))
                 optimizer.state[p] = {"step": torch.tensor(float(step)), "exp_avg": self.m[a][off:off + n].view(p.shape),
                                       "exp_avg_sq": self.v[a][off:off + n].view(p.shape)}
+                self.params.append(p)
         self.step = step
         self.optimizer = optimizer
         self._ptr0 = [p.data_ptr() for p in self.params[:1] + self.params[-1:]]
+
+    def shard_grad(self, shard_param) -> torch.Tensor:
+        for p, _a, off, n in self.shards:
+            if p is shard_param:
+                return self.g["shard"][off:off + n].view(p.shape)
+        raise KeyError("not a sharded table of this model")
 
     def valid(self) -> bool:
         """False after ``model.to()`` / ``load`` replaced parameter storage behind our back."""
         return [p.data_ptr() for p in self.params[:1] + self.params[-1:]] == self._ptr0
 
     def matches(self, prog: Program) -> bool:
-        return [(id(p), a, off, n) for p, (a, off, n) in zip(prog.params, prog.param_arena)] == self.layout
+        cur = [(id(p), a, off, n) for p, (a, off, n) in zip(prog.params, prog.param_arena)]
+        strip = lambda lst: [e for e in lst if e[1] != "virt"]      # noqa: E731  (virtual tables are per batch size)
+        return strip(cur) == strip(self.layout)
 
     def publish_step(self):
         """Write the step counter into ``optimizer.state`` (kept lazily: one Python loop per epoch, not per step)."""
@@ -126,8 +150,10 @@ class FusedTrainStep:
         self.dts = {c: x[c].dtype for c in cols}
         self.key = (self.B, tuple(self.dts.values()))
         b = ProgramBuilder(self.B, True)
-        model._lower(b, self.dts)
+        b.exchange = model._get_exchange()
+        model._lower(b, dict(self.dts))
         prog = b.finish()
+        self.exchange = b.exchange if prog.virtual_fields else None
         if prog.out_slot < 0:
             raise RuntimeError("the model's program has no head output")
         self.prog = prog
@@ -143,8 +169,9 @@ class FusedTrainStep:
         # ---- staging layout: [columns..., labels f32] ; scalars live in their own small ring
         self.layout = {}
         off = 0
+        vfields = {f.vcol: f for f in prog.virtual_fields}
         for name in prog.inputs:
-            if name == "__grad_out__":
+            if name == "__grad_out__" or name in vfields:
                 continue
             dt = self.dts[name]
             nbytes = self.B * torch.empty((), dtype=dt).element_size()
@@ -170,6 +197,10 @@ class FusedTrainStep:
         self._launched = [-1] * RING
         self._hold = [None] * RING          # caller buffers an in-flight async copy still reads
 
+        # gradients of the virtual tables are per batch size: this step owns them
+        self.g = dict(flat.g)
+        self.g["virt"] = torch.zeros(max(prog.arena_size.get("virt", 0), 4), dtype=torch.float32, device=device)
+        gsize = {a: self.g[a].numel() for a in self.g}
         # ---- slot table: the program's slots + trainer extras
         ns = len(prog.slot_desc)
         X = {"label": ns, "loss": ns + 1, "ctrl": ns + 2, "hyper": ns + 3}
@@ -184,18 +215,21 @@ class FusedTrainStep:
         for name, slot in prog.inputs.items():
             if name == "__grad_out__":
                 ptrs[slot] = self.gout.data_ptr()
+            elif name in vfields:
+                ptrs[slot] = vfields[name].vidx.data_ptr()
             else:
                 ptrs[slot] = base + self.layout[name][0]
         for i, d in enumerate(prog.slot_desc):
             if d[0] == "grad":
-                ptrs[i] = flat.g[d[1]].data_ptr() + 4 * d[2]
+                ptrs[i] = self.g[d[1]].data_ptr() + 4 * d[2]
         ptrs[X["label"]] = base + self.y_off
         ptrs[X["loss"]] = self.loss_ring_dev.data_ptr()
         ptrs[X["hyper"]] = self.dev_scal.data_ptr()
         ptrs[X["ctrl"]] = self.dev_scal.data_ptr() + 32
         for a, (sp, sg, sm, sv) in self.arena_slots.items():
-            ptrs[sp], ptrs[sg], ptrs[sm], ptrs[sv] = (flat.p[a].data_ptr(), flat.g[a].data_ptr(), flat.m[a].data_ptr(),
-                                                      flat.v[a].data_ptr())
+            ptrs[sg] = self.g[a].data_ptr()
+            if a in flat.opt_arenas:
+                ptrs[sp], ptrs[sm], ptrs[sv] = flat.p[a].data_ptr(), flat.m[a].data_ptr(), flat.v[a].data_ptr()
         self.ptrs = ptrs
 
         # ---- record lists
@@ -211,13 +245,24 @@ class FusedTrainStep:
 
         split = ProgramBuilder._split64
         bce = rec(N.OP_BCE, [self.B, N.DT_F32, RING], [prog.out_slot, X["label"], prog.gout_slot, X["loss"], X["ctrl"]])
-        zeros = [rec(N.OP_ZERO, split(4 * flat.size[a]), [self.arena_slots[a][1]]) for a in flat.size]
-        adams = [rec(N.OP_ADAM, [*split(flat.size[a]), 0], [*self.arena_slots[a], X["hyper"]]) for a in flat.size]
+        zeros = [rec(N.OP_ZERO, split(4 * gsize[a]), [self.arena_slots[a][1]]) for a in flat.size]
+        adams = [rec(N.OP_ADAM, [*split(flat.size[a]), 0], [*self.arena_slots[a], X["hyper"]]) for a in flat.opt_arenas
+                 if flat.size[a] > 4 or a == "dense"]
         stack = lambda lst: np.stack(lst).astype(N.REC_DTYPE)      # noqa: E731
         self.recs_a = np.concatenate([prog.recs_fwd, stack([bce] + zeros), prog.recs_bwd])
         self.recs_b = stack(adams)
-        if grad_sync is None:
+        if grad_sync is None and self.exchange is None:
             self.recs_a, self.recs_b = np.concatenate([self.recs_a, self.recs_b]), None
+        # typed views of the staged index columns of row-sharded fields + the gradient views the exchange routes
+        self._vf = []
+        for f in prog.virtual_fields:
+            o, nb, _npdt = self.layout[f.name]
+            idx = self.dev_stage[o:o + nb].view(self.dts[f.name])
+            gv = None
+            for p_, (a, off_, n_) in zip(prog.params, prog.param_arena):
+                if p_ is f.virt:
+                    gv = self.g["virt"][off_:off_ + n_].view(f.virt.shape)
+            self._vf.append((f, idx, gv, flat.shard_grad(f.shard) if f.shard.requires_grad else None))
         self.n_launch = (sum(1 for r in self.recs_a if int(r["kind"]) != N.OP_GROUP) +
                          (0 if self.recs_b is None else len(self.recs_b)))
         self.graph = None
@@ -227,9 +272,15 @@ class FusedTrainStep:
     # ---- device work of one step (graph-capturable: no syncs, no allocations) ------------------------
     def _body(self):
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        for f, idx, _gv, _gs in self._vf:              # embedding exchange, forward half (NCCL over NVLink)
+            self.exchange.lookup(f, idx)
         N.program_run(self.recs_a, self.ptrs, stream)
         if self.recs_b is not None:
-            self.grad_sync(self.flat.g)
+            for f, _idx, gv, gs in self._vf:           # backward half: route virtual-table gradients to their owners
+                if gv is not None and gs is not None:
+                    self.exchange.route_grad(f, gv, gs)
+            if self.grad_sync is not None:
+                self.grad_sync(self.flat.g)
             N.program_run(self.recs_b, self.ptrs, stream)
         N.memcpy_async(self.loss_ring_host.data_ptr(), self.loss_ring_dev.data_ptr(), 4 * RING, stream)
 
@@ -322,4 +373,6 @@ class FusedTrainStep:
             raise RuntimeError("loss handle expired: more than %d steps were launched since" % RING)
         self.done_ev[slot].synchronize()
         self.runner.check_indices()
+        if self.exchange is not None:
+            self.exchange.check_indices()
         return float(self.loss_ring_host[slot])
