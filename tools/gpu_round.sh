@@ -8,6 +8,6 @@ python bench.py --steps 100 --warmup 10 > gpurun_out/${TAG}_bench.json 2> gpurun
 python bench.py --impl reference --steps 10 --warmup 2 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:${KRE} -s 40 -c 3 -f -o gpurun_out/${TAG}_prof \
+ncu --set full --clock-control none --import-source on -k regex:${KRE} -s ${4:-40} -c ${3:-3} -f -o gpurun_out/${TAG}_prof \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1
 tail -3 gpurun_out/${TAG}_pytest.log; cat gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err
