@@ -1,0 +1,162 @@
+// swr_tc.cuh -- sm_100a tensor-core plumbing for the grouped FC kernels (swr_fc_tc.cu):
+// mbarrier, TMEM allocation, tcgen05.mma (kind::tf32) issue, tcgen05.ld, and the shared-memory
+// operand layouts + matrix descriptors the MMA unit reads.
+//
+// Operand tiles are staged by the CTA's own threads (the operands are *computed* while staging:
+// lazy BatchNorm + activation, BatchNorm-backward affine map, STAR weight product, hi/lo TF32
+// split), so there is no TMA here; the tiles are written straight in the canonical 128-byte
+// swizzled layouts:
+//   K-major  (contraction contiguous): row r (an M or N index) owns 128 B = 32 fp32 of contraction;
+//            16-byte chunk j of row r sits at r*128 + ((j ^ (r & 7)) << 4); 8 rows = one 1024 B atom.
+//            (SWIZZLE_128B, 16-byte base)
+//   MN-major (M/N index contiguous):   32-bit operands use the 128-byte swizzle with a 32-byte base
+//            (SWIZZLE_128B_BASE32B): a 128 B row holds 32 consecutive M/N indices of one contraction
+//            index c, rows of a 32-wide M/N group are contiguous over c ([M/N group][32 c][128 B]), and the
+//            32-byte unit u of row c sits at unit (u ^ (c & 3)).  A swizzle atom is 4 rows = 512 B.
+// One tcgen05.mma of kind::tf32 contracts 8 elements: 32 B of a K-major row, or 8 rows (1024 B)
+// of an MN-major group.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace swr {
+namespace tc {
+
+constexpr int KBLK = 32;            // contraction elements per pipeline stage (= one 128 B swizzle row)
+constexpr int UMMA_K = 8;           // contraction elements per tcgen05.mma.kind::tf32
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ---------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a descriptor or protocol bug must surface as a trapped kernel (an error the host
+// reports), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+
+// ---- TMEM / tcgen05 ---------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {   // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {     // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (the MMA unit)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// all previously issued MMAs of this thread arrive on `bar` when they complete
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, one thread issues
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives lane (lane_base + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- descriptors --------------------------------------------------------------------------------
+// Shared-memory matrix descriptor (SWIZZLE_128B): start address, leading / stride byte offsets in
+// 16-byte units, descriptor version 1 (sm_100), layout type 2 at bits [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+// K-major tile, k-step ks (8 contraction elements = 32 B inside the 128 B swizzle row)
+__device__ __forceinline__ uint64_t kmajor_desc(uint32_t tile_saddr, int ks) {
+  return make_smem_desc(tile_saddr + ks * (UMMA_K * 4), 16, 1024);
+}
+// MN-major tile, k-step ks = contraction rows [8 ks, 8 ks + 8): leading offset = stride between 32-wide M/N
+// groups (KBLK rows of 128 B), stride offset = stride between 4-row swizzle atoms along the contraction.
+__device__ __forceinline__ uint64_t mnmajor_desc(uint32_t tile_saddr, int ks, int variant = 0) {
+  const uint32_t grp = KBLK * 128u;
+  return variant == 0 ? make_smem_desc(tile_saddr + ks * 1024u, grp, 512, 1) : make_smem_desc(tile_saddr + ks * 1024u, 512, grp, 1);
+}
+// Instruction descriptor: fp32 accumulate, TF32 x TF32, dense, M x N, operand majors.
+__host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- tile addressing ------------------------------------------------------------------------------
+// byte offset of 16-byte chunk `chunk` (4 contraction elements) of row `row` in a K-major tile
+__device__ __forceinline__ uint32_t kmajor_off(int row, int chunk) { return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4); }
+// byte offset of the 16-byte chunk holding M/N indices [4q, 4q+4) of contraction row c (0..31) in an MN-major tile
+__device__ __forceinline__ uint32_t mnmajor_off(int q, int c) {
+  return (uint32_t)((q >> 3) * (KBLK * 128) + c * 128 + (((((q & 7) >> 1) ^ (c & 3)) << 5) | ((q & 1) << 4)));
+}
+
+// ---- TF32 split -------------------------------------------------------------------------------------
+// x = hi + lo with hi = rna_tf32(x) and lo = rna_tf32(x - hi): A*B ~= Ahi*Bhi + Ahi*Blo + Alo*Bhi keeps
+// fp32-level accuracy (the dropped lo*lo term is 2^-22 relative).
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  const float r = x - hi;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
+  lo = __uint_as_float(l);
+}
+__device__ __forceinline__ void store_split(uint8_t* hi_tile, uint8_t* lo_tile, uint32_t off, float4 v) {
+  float4 h, l;
+  split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+  *reinterpret_cast<float4*>(hi_tile + off) = h;
+  *reinterpret_cast<float4*>(lo_tile + off) = l;
+}
+
+}  // namespace tc
+}  // namespace swr
