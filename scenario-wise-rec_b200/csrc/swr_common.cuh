@@ -148,6 +148,25 @@ __device__ __forceinline__ float load_scalar(const void* p, int dtype, int64_t i
   }
 }
 
+__device__ __forceinline__ bool is_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// rows [.., R) x cols [c, c+4) of a row-major matrix, zero outside
+__device__ __forceinline__ float4 load4_guard(const float* __restrict__ base, int64_t ld, int r, int c, int R, int C, bool vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r < R && c < C) {
+    const float* p = base + (int64_t)r * ld + c;
+    if (vec && c + 3 < C) {
+      v = *reinterpret_cast<const float4*>(p);
+    } else {
+      v.x = p[0];
+      if (c + 1 < C) v.y = p[1];
+      if (c + 2 < C) v.z = p[2];
+      if (c + 3 < C) v.w = p[3];
+    }
+  }
+  return v;
+}
+
 // ---- host side -----------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);

@@ -45,25 +45,6 @@ struct FcParams {
   int dst_tile[kMaxGroups + 1];
 };
 
-__device__ __forceinline__ bool is_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-
-// rows [.., R) x cols [c, c+4) of a row-major matrix, zero outside
-__device__ __forceinline__ float4 load4_guard(const float* __restrict__ base, int64_t ld, int r, int c, int R, int C, bool vec) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (r < R && c < C) {
-    const float* p = base + (int64_t)r * ld + c;
-    if (vec && c + 3 < C) {
-      v = *reinterpret_cast<const float4*>(p);
-    } else {
-      v.x = p[0];
-      if (c + 1 < C) v.y = p[1];
-      if (c + 2 < C) v.z = p[2];
-      if (c + 3 < C) v.w = p[3];
-    }
-  }
-  return v;
-}
-
 template <class C>
 __device__ __forceinline__ void mma_tile(const float* __restrict__ As, const float* __restrict__ Bs, int ty, int tx,
                                          float (&acc)[C::TM][C::TN], float* rowsum) {
@@ -612,6 +593,7 @@ int launch_fc_fwd(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t s
   int nmax = 0; int64_t cols = 0;
   for (int g = 0; g < n_groups; ++g) { p.g[g] = groups[g]; nmax = max(nmax, groups[g].Y.n); cols += groups[g].Y.n; }
   p.n_groups = n_groups; p.B = (int)B; p.inv_count = 1.0f / (float)B;
+  if (fc_tc_wanted(groups, n_groups, B)) return launch_fc_tc_fwd(groups, n_groups, B, st);
   if (nmax > 16) {
     const int64_t tiles128 = (int64_t)ceil_div(B, 128) * ((cols + 63) / 64);
     return tiles128 >= 296 ? run_fwd<CfgWide>(p, st) : run_fwd<CfgMid>(p, st);
@@ -664,6 +646,7 @@ int launch_fc_dgrad(const FcGroup* groups, const int* dst_of, int n_groups, int6
   p.dst_group[n_dst] = n_groups;
   p.n_dst = n_dst;
   p.n_groups = n_groups; p.B = (int)B; p.inv_count = 1.0f / (float)B;
+  if (fc_tc_wanted(groups, n_groups, B)) return launch_fc_tc_dgrad(groups, p.dst_group, n_dst, n_groups, B, st);
   if (kd_max > 16) return tiles128 >= 296 ? run_dgrad<CfgWide>(p, st) : run_dgrad<CfgMid>(p, st);
   return run_dgrad<CfgNarrowS>(p, st);
 }
@@ -701,6 +684,7 @@ int launch_fc_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t
     if (!groups[g].Y.dz) { set_error("fc_wgrad: group %d has no output gradient buffer", g); return SWR_ERR_INVALID; }
   }
   p.n_groups = n_groups; p.B = (int)B; p.inv_count = 1.0f / (float)B;
+  if (fc_tc_wanted(groups, n_groups, B)) return launch_fc_tc_wgrad(groups, n_groups, B, st);
   return kmax > 16 ? run_wgrad<CfgMid>(p, st) : run_wgrad<CfgNarrowS>(p, st);
 }
 

@@ -43,6 +43,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // Bounded wait: a descriptor or protocol bug must surface as a trapped kernel (an error the host
 // reports), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -141,21 +144,26 @@ __device__ __forceinline__ uint32_t mnmajor_off(int q, int c) {
 }
 
 // ---- TF32 split -------------------------------------------------------------------------------------
-// x = hi + lo with hi = rna_tf32(x) and lo = rna_tf32(x - hi): A*B ~= Ahi*Bhi + Ahi*Blo + Alo*Bhi keeps
-// fp32-level accuracy (the dropped lo*lo term is 2^-22 relative).
+// x = hi + lo with hi = x rounded to TF32 (nearest, ties away: add half an ulp of the 10-bit mantissa and clear the
+// low 13 bits -- the same result as cvt.rna.tf32.f32, which sm_100a expands into a longer integer sequence) and
+// lo = x - hi (exact in fp32; the MMA unit reads the TF32 part of it).  A*B ~= Ahi*Bhi + Ahi*Blo + Alo*Bhi keeps
+// ~2^-21 relative accuracy per product (the dropped lo*lo term is 2^-22).
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  uint32_t h, l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
-  const float r = x - hi;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
-  lo = __uint_as_float(l);
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+  lo = x - hi;
 }
-__device__ __forceinline__ void store_split(uint8_t* hi_tile, uint8_t* lo_tile, uint32_t off, float4 v) {
+__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// hi_tile / lo_tile / off: shared-space byte addresses
+__device__ __forceinline__ void store_split(uint32_t hi_tile, uint32_t lo_tile, uint32_t off, float4 v) {
   float4 h, l;
   split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-  *reinterpret_cast<float4*>(hi_tile + off) = h;
-  *reinterpret_cast<float4*>(lo_tile + off) = l;
+  sts128(hi_tile + off, h);
+  sts128(lo_tile + off, l);
+}
+__device__ __forceinline__ void store_split(uint8_t* hi_tile, uint8_t* lo_tile, uint32_t off, float4 v) {
+  store_split(smem_u32(hi_tile), smem_u32(lo_tile), off, v);
 }
 
 }  // namespace tc
