@@ -61,6 +61,14 @@ SWR_API const char* swr_last_error(void);
 SWR_API int64_t swr_launch_count(void);
 /* 0 if the current device is sm_100-class, else SWR_ERR_NO_DEVICE */
 SWR_API int swr_device_check(void);
+/* Arithmetic of the grouped FC ops (the reference's nn.Linear contractions, basic/layers.py:254):
+ *   SWR_FC_SIMT  fp32 FFMA kernels (round-to-nearest accumulate, the numerics of a stock fp32 GPU run)
+ *   SWR_FC_TC    tcgen05 3xTF32 kernels for every layer whose shape they accept
+ *   SWR_FC_AUTO  tcgen05 for the wide layers, FFMA for the narrow ones (default; env SWR_FC_TC=0|1|2 presets it)
+ * Process-wide; takes effect for programs run (or CUDA graphs captured) afterwards.  Returns the previous mode. */
+typedef enum { SWR_FC_SIMT = 0, SWR_FC_TC = 1, SWR_FC_AUTO = 2 } swr_fc_mode;
+SWR_API int swr_set_fc_mode(int mode);
+SWR_API int swr_get_fc_mode(void);
 
 /* Per-op device timing of swr_program_run (bench.py's live roofline measurement).
  * swr_profile_begin(): every op of the program runs issued by this process (any thread) from now

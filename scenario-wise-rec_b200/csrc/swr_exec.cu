@@ -294,6 +294,9 @@ SWR_API int swr_abi_version(void) { return SWR_ABI_VERSION; }
 SWR_API const char* swr_last_error(void) { return g_err; }
 SWR_API int64_t swr_launch_count(void) { return g_launches.load(); }
 
+SWR_API int swr_set_fc_mode(int mode) { return fc_mode_set(mode); }
+SWR_API int swr_get_fc_mode(void) { return fc_mode_get(); }
+
 SWR_API int swr_device_check(void) {
   int dev = 0;
   cudaDeviceProp prop;

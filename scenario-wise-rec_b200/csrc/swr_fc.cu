@@ -585,15 +585,41 @@ static int run_fwd(FcParams& p, cudaStream_t st) {
   return SWR_OK;
 }
 
+// SWR_FC_AUTO: groups too narrow to fill a 128 x N accumulator tile (gates, towers' last layers) stay on the
+// FFMA kernels -- as CTAs of the tensor-core launch they would each hold a whole SM for a sliver of work.
+static bool tc_narrow(const FcGroup& g) { return g.Y.n < 32; }
+
+template <class F1, class F2>
+static int split_by_width(const FcGroup* groups, int n_groups, F1 run_tc, F2 run_simt) {
+  FcGroup wide[kMaxGroups], narrow[kMaxGroups];
+  int nw = 0, nn = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    if (fc_mode_get() == SWR_FC_AUTO && tc_narrow(groups[g])) narrow[nn++] = groups[g];
+    else wide[nw++] = groups[g];
+  }
+  if (nn) { int rc = run_simt(narrow, nn); if (rc) return rc; }
+  if (nw) { int rc = run_tc(wide, nw); if (rc) return rc; }
+  return SWR_OK;
+}
+
+static int launch_fc_fwd_simt(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st);
+static int launch_fc_wgrad_simt(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st);
+
 int launch_fc_fwd(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st) {
   if (B <= 0) return SWR_OK;
   int rc = check_groups(groups, n_groups, "fc_fwd");
   if (rc) return rc;
+  if (fc_tc_wanted(groups, n_groups, B))
+    return split_by_width(groups, n_groups, [&](const FcGroup* g, int n) { return launch_fc_tc_fwd(g, n, B, st); },
+                          [&](const FcGroup* g, int n) { return launch_fc_fwd_simt(g, n, B, st); });
+  return launch_fc_fwd_simt(groups, n_groups, B, st);
+}
+
+static int launch_fc_fwd_simt(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st) {
   FcParams p{};
   int nmax = 0; int64_t cols = 0;
   for (int g = 0; g < n_groups; ++g) { p.g[g] = groups[g]; nmax = max(nmax, groups[g].Y.n); cols += groups[g].Y.n; }
   p.n_groups = n_groups; p.B = (int)B; p.inv_count = 1.0f / (float)B;
-  if (fc_tc_wanted(groups, n_groups, B)) return launch_fc_tc_fwd(groups, n_groups, B, st);
   if (nmax > 16) {
     const int64_t tiles128 = (int64_t)ceil_div(B, 128) * ((cols + 63) / 64);
     return tiles128 >= 296 ? run_fwd<CfgWide>(p, st) : run_fwd<CfgMid>(p, st);
@@ -677,6 +703,15 @@ int launch_fc_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t
   if (B <= 0) return SWR_OK;
   int rc = check_groups(groups, n_groups, "fc_wgrad");
   if (rc) return rc;
+  for (int g = 0; g < n_groups; ++g)
+    if (!groups[g].Y.dz) { set_error("fc_wgrad: group %d has no output gradient buffer", g); return SWR_ERR_INVALID; }
+  if (fc_tc_wanted(groups, n_groups, B))
+    return split_by_width(groups, n_groups, [&](const FcGroup* g, int n) { return launch_fc_tc_wgrad(g, n, B, st); },
+                          [&](const FcGroup* g, int n) { return launch_fc_wgrad_simt(g, n, B, st); });
+  return launch_fc_wgrad_simt(groups, n_groups, B, st);
+}
+
+static int launch_fc_wgrad_simt(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st) {
   FcParams p{};
   int kmax = 0;
   for (int g = 0; g < n_groups; ++g) {
@@ -684,7 +719,6 @@ int launch_fc_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t
     if (!groups[g].Y.dz) { set_error("fc_wgrad: group %d has no output gradient buffer", g); return SWR_ERR_INVALID; }
   }
   p.n_groups = n_groups; p.B = (int)B; p.inv_count = 1.0f / (float)B;
-  if (fc_tc_wanted(groups, n_groups, B)) return launch_fc_tc_wgrad(groups, n_groups, B, st);
   return kmax > 16 ? run_wgrad<CfgMid>(p, st) : run_wgrad<CfgNarrowS>(p, st);
 }
 

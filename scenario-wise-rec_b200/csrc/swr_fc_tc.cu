@@ -21,6 +21,8 @@
 #include "swr_common.cuh"
 #include "swr_launch.h"
 #include "swr_tc.cuh"
+#include <atomic>
+#include <cstdio>
 #include <cstdlib>
 
 namespace swr {
@@ -44,6 +46,7 @@ struct TcParams {
   int stages;
   int splits;                      // wgrad: batch splits
   int rows_per_split;
+  long long* dbg;                  // development aid: per-phase cycle counts of CTA 0 (null in production)
   int n_dst;                       // dgrad
   int dst_group[kMaxGroups + 1];
   int dst_tile[kMaxGroups + 1];
@@ -75,17 +78,19 @@ __device__ __forceinline__ uint32_t tc_setup(TcShared& sh, int stages, int nt, i
   return sh.tmem_base;
 }
 
-// one pipeline stage worth of MMAs (4 k-steps x 3 split products), issued by one thread
+// one pipeline stage worth of MMAs (4 k-steps x 3 split products), issued by one thread.  Descriptors differ between
+// k-steps only in the start address (low word): +32 B per step in a K-major tile, +1024 B in an MN-major one.
 __device__ __forceinline__ void tc_issue(uint32_t tmem, uint32_t stage_saddr, uint32_t b_bytes, bool a_mn, bool b_mn, uint32_t idesc, bool first) {
   const uint32_t ah = stage_saddr, al = ah + TC_A_BYTES, bh = al + TC_A_BYTES, bl = bh + b_bytes;
+  const uint64_t dah0 = a_mn ? mnmajor_desc(ah, 0) : kmajor_desc(ah, 0);
+  const uint64_t dbh0 = b_mn ? mnmajor_desc(bh, 0) : kmajor_desc(bh, 0);
+  const uint64_t a_lo_d = (uint64_t)(TC_A_BYTES >> 4), b_lo_d = (uint64_t)(b_bytes >> 4);   // hi tile -> lo tile
+  const uint64_t a_step = a_mn ? (1024u >> 4) : ((UMMA_K * 4) >> 4), b_step = b_mn ? (1024u >> 4) : ((UMMA_K * 4) >> 4);
 #pragma unroll
   for (int ks = 0; ks < KBLK / UMMA_K; ++ks) {
-    const uint64_t dah = a_mn ? mnmajor_desc(ah, ks) : kmajor_desc(ah, ks);
-    const uint64_t dal = a_mn ? mnmajor_desc(al, ks) : kmajor_desc(al, ks);
-    const uint64_t dbh = b_mn ? mnmajor_desc(bh, ks) : kmajor_desc(bh, ks);
-    const uint64_t dbl = b_mn ? mnmajor_desc(bl, ks) : kmajor_desc(bl, ks);
-    mma_tf32(tmem, dal, dbh, idesc, (first && ks == 0) ? 0u : 1u);
-    mma_tf32(tmem, dah, dbl, idesc, 1u);
+    const uint64_t dah = dah0 + ks * a_step, dbh = dbh0 + ks * b_step;
+    mma_tf32(tmem, dah + a_lo_d, dbh, idesc, (first && ks == 0) ? 0u : 1u);
+    mma_tf32(tmem, dah, dbh + b_lo_d, idesc, 1u);
     mma_tf32(tmem, dah, dbh, idesc, 1u);
   }
 }
@@ -157,104 +162,85 @@ __device__ __forceinline__ float4 mul4(float4 a, float4 b) { return make_float4(
 __device__ __forceinline__ float4 ld4s(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
-// first n (1..3, or 4 unaligned) floats at p, the rest zero: tile edges only, kept out of line
-__device__ __noinline__ float4 ld_partial(const float* __restrict__ p, int n) {
-  float4 v = zero4();
-  v.x = __ldg(p);
+// ---- what one thread moves per k-block ---------------------------------------------------------------------
+// An operand tile is 32 contraction elements x R rows (R = 128 for the accumulator-row operand, NT rounded up to 64 for
+// the accumulator-column operand) = R * 8 float4; thread tid moves float4 number it * 512 + tid of it, it < R / 64.
+//   K-major  (source rows = M/N index, contraction contiguous): row it*64 + (tid >> 3), contraction chunk tid & 7
+//   MN-major (source rows = contraction index, M/N contiguous): contraction row c = v / nq, M/N quad q = v % nq, nq = R / 4
+// Fast path (interior k-blocks of 16-byte aligned sources): one unconditional 16-byte load per float4 from a pointer
+// fixed at kernel start and advanced by a constant per k-block.  Rows / quads outside the matrix are clamped onto
+// the last valid one instead of predicated: they only produce accumulator rows / columns that are never stored.
+// Slow path (the last, partial k-block of a contraction; unaligned or odd-width sources): guarded loads, zero fill.
+template <int IT>
+struct Op {
+  const float* p[IT];   // fast-path source pointer for k-block 0
+  uint32_t so[IT];      // shared-memory byte offset inside the tile
+};
+template <int IT>
+__device__ __forceinline__ void op_init_k(Op<IT>& o, const float* base, int ld, int row0, int row_end, int nit, int tid) {
+  const int cj = tid & 7, r0 = tid >> 3;
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int r = it * TC_RPI + r0;
+    const int rc = min(row0 + r, row_end - 1);
+    o.p[it] = base + (int64_t)rc * ld + 4 * cj;
+    o.so[it] = kmajor_off(r, cj);
+  }
+}
+template <int IT>
+__device__ __forceinline__ void op_init_m(Op<IT>& o, const float* base /* source + first M/N index of the tile */, int ld, int mn_len, int nq, int nit, int tid) {
+  const int qmax = max(mn_len / 4 - 1, 0);
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    if (it < nit) {
+      const int v = it * TC_NP + tid;
+      const int c = v / nq, q = v - c * nq;
+      o.p[it] = base + (int64_t)c * ld + 4 * min(q, qmax);
+      o.so[it] = mnmajor_off(q, c);
+    } else { o.p[it] = base; o.so[it] = 0; }
+  }
+}
+template <int IT>
+__device__ __forceinline__ void op_load_fast(const Op<IT>& o, int64_t adv, int nit, float4 (&r)[IT]) {
+#pragma unroll
+  for (int it = 0; it < IT; ++it)
+    if (it < nit) r[it] = __ldg(reinterpret_cast<const float4*>(o.p[it] + adv));
+}
+// first n (0..4) floats at p, the rest zero
+__device__ __noinline__ float4 ld_guard(const float* __restrict__ p, int n, bool vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n == 4 && vec) return __ldg(reinterpret_cast<const float4*>(p));
+  if (n > 0) v.x = __ldg(p);
   if (n > 1) v.y = __ldg(p + 1);
   if (n > 2) v.z = __ldg(p + 2);
   if (n > 3) v.w = __ldg(p + 3);
   return v;
 }
-// first n (0..4) floats at p, the rest zero; one 16-byte read-only load when everything is there and aligned
-__device__ __forceinline__ float4 ldn(const float* __restrict__ p, int n, bool vec) {
-  float4 v = zero4();
-  if (n == 4 && vec) v = __ldg(reinterpret_cast<const float4*>(p));
-  else if (n > 0) v = ld_partial(p, n);
-  return v;
-}
-
-// ---- what one thread moves per k-block ---------------------------------------------------------------------
-// K-major operand (source rows = M/N index, contraction contiguous): chunk cj = tid & 7 of rows it*64 + (tid >> 3).
-struct KSlice {
-  const float* p0;      // element (row0 + r0, 4 cj) of the source
-  int64_t rstride;      // 64 * ld
-  uint32_t so0;         // shared-memory offset of (r0, cj); row it*64 + r0 is 8192 B further per it
-  uint32_t rowmask;     // bit it: row it*64 + r0 exists (inside the tile and inside the matrix)
-  int cj4;              // 4 * cj
-};
-__device__ __forceinline__ KSlice make_kslice(const float* base, int ld, int row0, int row_end, int tile_rows, int tid, int its) {
-  KSlice s;
+// K-major slow path: rows [row0, row_end) x contraction [c0, c_len) of base[., ld]
+template <int IT>
+__device__ __forceinline__ void op_load_slow_k(const float* base, int ld, int row0, int row_end, int c0, int c_len, bool vec, int nit, int tid, float4 (&r)[IT]) {
   const int cj = tid & 7, r0 = tid >> 3;
-  s.p0 = base + (int64_t)(row0 + r0) * ld + 4 * cj;
-  s.rstride = (int64_t)TC_RPI * ld;
-  s.so0 = kmajor_off(r0, cj);
-  s.cj4 = 4 * cj;
-  s.rowmask = 0;
-  for (int it = 0; it < its; ++it) {
-    const int r = it * TC_RPI + r0;
-    if (r < tile_rows && row0 + r < row_end) s.rowmask |= 1u << it;
-  }
-  return s;
-}
-// contraction elements [kb*32 + 4cj, +4) of every row of the slice; c_len = contraction length
-template <int IT>
-__device__ __forceinline__ void kslice_load(const KSlice& s, const float* __restrict__ p0, float4 (&r)[IT], int kb, int c_len, bool vec) {
-  int dyn = c_len - kb * KBLK - s.cj4;
+  int dyn = c_len - c0 - 4 * cj;
   dyn = dyn < 0 ? 0 : (dyn > 4 ? 4 : dyn);
-  const float* pk = p0 + kb * KBLK;
 #pragma unroll
-  for (int it = 0; it < IT; ++it) r[it] = ldn(pk + it * s.rstride, ((s.rowmask >> it) & 1u) ? dyn : 0, vec);
-}
-
-// MN-major operand (source rows = contraction index, M/N contiguous): float4 v = it*512 + tid -> contraction row
-// c = v / nq, M/N quad q = v % nq  (nq = quads per contraction row of the tile).
-template <int IT>
-struct MSlice {
-  int32_t goff[IT];     // c * ld + 4 q
-  uint32_t so[IT];      // shared-memory offset
-  uint32_t nv;          // 4 bits per it: valid floats along M/N (0..4), 15 = outside the tile (nothing to store)
-  uint32_t cpack;       // 5 bits per it: c
-  uint32_t qpack;       // 8 bits per it: q
-  int64_t kstride;      // 32 * ld
-};
-template <int IT>
-__device__ __forceinline__ MSlice<IT> make_mslice(int ld, int mn0, int mn_end, int nq, int tid) {
-  static_assert(IT <= 4, "packed fields hold 4 entries");
-  MSlice<IT> s;
-  s.nv = 0; s.cpack = 0; s.qpack = 0; s.kstride = (int64_t)32 * ld;
-#pragma unroll
-  for (int it = 0; it < IT; ++it) {
-    const int v = it * TC_NP + tid;
-    const int c = v / nq, q = v - c * nq;
-    uint32_t n = 15;
-    if (c < KBLK) {
-      int k = mn_end - (mn0 + 4 * q);
-      n = (uint32_t)(k < 0 ? 0 : (k > 4 ? 4 : k));
-      s.goff[it] = c * ld + 4 * q;
-      s.so[it] = mnmajor_off(q, c);
-      s.cpack |= (uint32_t)c << (5 * it);
-      s.qpack |= (uint32_t)q << (8 * it);
-    } else {
-      s.goff[it] = 0; s.so[it] = 0;
+  for (int it = 0; it < IT; ++it)
+    if (it < nit) {
+      const int row = row0 + it * TC_RPI + r0;
+      r[it] = ld_guard(base + (int64_t)row * ld + c0 + 4 * cj, row < row_end ? dyn : 0, vec);
     }
-    s.nv |= n << (4 * it);
-  }
-  return s;
 }
-// base = source + mn0 (first M/N index of the tile) + c0 * ld (first contraction row of k-block 0); c_rows = rows left from c0
+// MN-major slow path: contraction rows [c0, c_len) x M/N [mn0, mn_end) of base[., ld]
 template <int IT>
-__device__ __forceinline__ void mslice_load(const MSlice<IT>& s, const float* __restrict__ base, float4 (&r)[IT], int kb, int c_rows, bool vec) {
-  const int left = c_rows - kb * KBLK;   // contraction rows still inside the matrix
-  const float* pk = base + kb * s.kstride;
+__device__ __forceinline__ void op_load_slow_m(const float* base, int ld, int mn0, int mn_end, int c0, int c_len, int nq, bool vec, int nit, int tid, float4 (&r)[IT]) {
 #pragma unroll
-  for (int it = 0; it < IT; ++it) {
-    const uint32_t nv = (s.nv >> (4 * it)) & 15u;
-    if (nv != 15u) {
-      const int c = (int)((s.cpack >> (5 * it)) & 31u);
-      r[it] = ldn(pk + s.goff[it], c < left ? (int)nv : 0, vec);
+  for (int it = 0; it < IT; ++it)
+    if (it < nit) {
+      const int v = it * TC_NP + tid;
+      const int c = v / nq, q = v - c * nq;
+      int n = mn_end - (mn0 + 4 * q);
+      n = n < 0 ? 0 : (n > 4 ? 4 : n);
+      r[it] = ld_guard(base + (int64_t)(c0 + c) * ld + mn0 + 4 * q, (c0 + c < c_len) ? n : 0, vec);
     }
-  }
 }
 
 // max(z, slope * z): relu (slope 0), identity (1), leaky (0.1); sigmoid handled apart
@@ -279,6 +265,7 @@ __device__ __forceinline__ float4 affine4(float4 c0, float4 dz, float4 c1, float
 // forward:  Y[m, n] = sum_k act(norm(A))[m, k] * Weff[n, k] + beff[n]
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_NT, 1) fc_tc_fwd_kernel(const __grid_constant__ TcParams p) {
+  const long long t_kernel = clock64();
   extern __shared__ uint8_t smem_raw[];
   __shared__ TcShared sh;
   uint8_t* smem = align1024(smem_raw);
@@ -289,12 +276,12 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_fwd_kernel(const __grid_consta
   while (g + 1 < p.n_groups && p.tile_start[g + 1] <= (int)blockIdx.x) ++g;
   const FcGroup& G = p.g[g];
   const int M = p.B, N = G.Y.n, K = G.A.n;
-  const int NT = p.nt[g], NTp = (NT + 31) & ~31, nq = NTp >> 2;
+  const int NT = p.nt[g], NTr = (NT + 63) & ~63, nq = NTr >> 2, nitb = NTr >> 6;
   const int nt_n = (N + NT - 1) / NT;
   const int local = blockIdx.x - p.tile_start[g];
   const int m0 = (local / nt_n) * TC_BM, n0 = (local % nt_n) * NT;
   const int nkb = (K + KBLK - 1) / KBLK, Kpad = nkb * KBLK;
-  const uint32_t b_bytes = (uint32_t)NTp * 128u, stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
+  const uint32_t b_bytes = (uint32_t)NTr * 128u, stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
   const int S = p.stages;
   float* kc = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes);   // [3][Kpad]: mu, s, b of the input columns
 
@@ -312,61 +299,77 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_fwd_kernel(const __grid_consta
   const int Nend = min(N, n0 + NT);
   const bool vecA = is_al16(G.A.raw) && (G.A.ld % 4 == 0);
   const bool vecW = is_al16(G.W) && (G.ldw % 4 == 0) && (!G.W2 || is_al16(G.W2));
+  const bool fastB = vecW && (!kn || ((Nend - n0) % 4 == 0));
   const bool hasW2 = G.W2 != nullptr;
   const float slope = act_slope(G.A.act);
   const bool sigA = G.A.act == SWR_ACT_SIGMOID;
-  const KSlice sa = make_kslice(G.A.raw, G.A.ld, m0, M, TC_BM, tid, 2);
-  KSlice sbk{};          // W [N, K] -> K-major tile
-  MSlice<4> sbm{};       // W [K, N] -> MN-major tile
-  const float* wbase = G.W;
-  if (!kn) sbk = make_kslice(G.W, G.ldw, n0, Nend, NT, tid, 4);
-  else { sbm = make_mslice<4>(G.ldw, n0, Nend, nq, tid); wbase += n0; }
   const int64_t w2diff = hasW2 ? (G.W2 - G.W) : 0;
+  Op<2> oa; Op<4> ob;
+  op_init_k<2>(oa, G.A.raw, G.A.ld, m0, M, 2, tid);
+  if (!kn) op_init_k<4>(ob, G.W, G.ldw, n0, Nend, nitb, tid);             // W [N, K] -> K-major tile
+  else op_init_m<4>(ob, G.W + n0, G.ldw, Nend - n0, nq, nitb, tid);       // W [K, N] -> MN-major tile
+  const int64_t bstep = kn ? (int64_t)KBLK * G.ldw : KBLK;
 
-  float4 ra[2], rb[4], rb2[4];
-  auto load = [&](int kb) {
-    kslice_load<2>(sa, sa.p0, ra, kb, K, vecA);
-    if (!kn) {
-      kslice_load<4>(sbk, sbk.p0, rb, kb, K, vecW);
-      if (hasW2) kslice_load<4>(sbk, sbk.p0 + w2diff, rb2, kb, K, vecW);
-    } else {
-      mslice_load<4>(sbm, wbase, rb, kb, K, vecW);
-      if (hasW2) mslice_load<4>(sbm, wbase + w2diff, rb2, kb, K, vecW);
-    }
+  // register prefetch one k-block ahead; W2 (STAR / M3oE only) is read at store time
+  struct Regs { float4 a[2], b[4]; };
+  auto load = [&](int kb, Regs& r) {
+    const bool interior = (kb + 1) * KBLK <= K;
+    if (vecA && interior) op_load_fast<2>(oa, (int64_t)kb * KBLK, 2, r.a);
+    else op_load_slow_k<2>(G.A.raw, G.A.ld, m0, M, kb * KBLK, K, vecA, 2, tid, r.a);
+    if (fastB && interior) op_load_fast<4>(ob, kb * bstep, nitb, r.b);
+    else if (!kn) op_load_slow_k<4>(G.W, G.ldw, n0, Nend, kb * KBLK, K, vecW, nitb, tid, r.b);
+    else op_load_slow_m<4>(G.W, G.ldw, n0, Nend, kb * KBLK, K, nq, vecW, nitb, tid, r.b);
   };
-  auto store = [&](int kb, uint32_t stage) {
+  auto store = [&](int kb, uint32_t stage, Regs& r) {
     const uint32_t ah = stage, al = ah + TC_A_BYTES, bh = al + TC_A_BYTES, bl = bh + b_bytes;
     if (plainA) {
 #pragma unroll
-      for (int it = 0; it < 2; ++it) store_split(ah, al, sa.so0 + it * (TC_RPI * 128), ra[it]);
+      for (int it = 0; it < 2; ++it) store_split(ah, al, oa.so[it], r.a[it]);
     } else {   // padded k: coefficients are 0 -> act(0) stays finite and meets a zero weight
-      const int k = kb * KBLK + sa.cj4;
+      const int k = kb * KBLK + 4 * (tid & 7);
       const float4 mu = ld4s(kc + k), sc = ld4s(kc + Kpad + k), bb = ld4s(kc + 2 * Kpad + k);
 #pragma unroll
-      for (int it = 0; it < 2; ++it) store_split(ah, al, sa.so0 + it * (TC_RPI * 128), norm_act4(ra[it], mu, sc, bb, slope, sigA));
+      for (int it = 0; it < 2; ++it) store_split(ah, al, oa.so[it], norm_act4(r.a[it], mu, sc, bb, slope, sigA));
     }
-    if (!kn) {
+    if (hasW2) {
+      float4 w2[4];
+      const bool interior = (kb + 1) * KBLK <= K;
+      if (fastB && interior) op_load_fast<4>(ob, kb * bstep + w2diff, nitb, w2);
+      else if (!kn) op_load_slow_k<4>(G.W2, G.ldw, n0, Nend, kb * KBLK, K, vecW, nitb, tid, w2);
+      else op_load_slow_m<4>(G.W2, G.ldw, n0, Nend, kb * KBLK, K, nq, vecW, nitb, tid, w2);
 #pragma unroll
       for (int it = 0; it < 4; ++it)
-        if (it * TC_RPI + (tid >> 3) < NT) store_split(bh, bl, sbk.so0 + it * (TC_RPI * 128), hasW2 ? mul4(rb[it], rb2[it]) : rb[it]);
-    } else {
-#pragma unroll
-      for (int it = 0; it < 4; ++it)
-        if (((sbm.nv >> (4 * it)) & 15u) != 15u) store_split(bh, bl, sbm.so[it], hasW2 ? mul4(rb[it], rb2[it]) : rb[it]);
+        if (it < nitb) r.b[it] = mul4(r.b[it], w2[it]);
     }
+#pragma unroll
+    for (int it = 0; it < 4; ++it)
+      if (it < nitb) store_split(bh, bl, ob.so[it], r.b[it]);
   };
 
   TcPipe pp; pp.init();
-  load(0);
+  Regs r0;
+  const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && (tid == 0 || tid == 33 || tid == 511);
+  long long t_acq = 0, t_store = 0, t_load = 0, t_pub = 0, t0 = 0, t_begin = dbg ? clock64() : 0;
+  load(0, r0);
   for (; pp.kb < nkb; pp.advance(S)) {
+    if (dbg) t0 = clock64();
     tc_acquire(sh, pp, S);
+    if (dbg) { const long long t = clock64(); t_acq += t - t0; t0 = t; }
     const uint32_t stage = smem_s + (uint32_t)pp.s * stage_bytes;
-    store(pp.kb, stage);
-    if (pp.kb + 1 < nkb) load(pp.kb + 1);
+    store(pp.kb, stage, r0);
+    if (dbg) { const long long t = clock64(); t_store += t - t0; t0 = t; }
+    if (pp.kb + 1 < nkb) load(pp.kb + 1, r0);
+    if (dbg) { const long long t = clock64(); t_load += t - t0; t0 = t; }
     tc_publish_issue(sh, pp, tmem, stage, b_bytes, nkb, false, kn, NT, tid);
+    if (dbg) { const long long t = clock64(); t_pub += t - t0; t0 = t; }
   }
+  const long long t_loop_end = dbg ? clock64() : 0;
   mbar_wait(&sh.bar_done, 0);
   fence_after_sync();
+  if (dbg) {
+    long long* o = p.dbg + (tid == 0 ? 0 : (tid == 33 ? 8 : 16));
+    o[0] = t_acq; o[1] = t_store; o[2] = t_load; o[3] = t_pub; o[4] = t_loop_end - t_begin; o[5] = clock64() - t_loop_end; o[6] = nkb; o[7] = t_begin - t_kernel;
+  }
 
   // ---- epilogue: bias, optional activation, store raw Y, fp64 column moments ----
   const int ldo = NT + 4;
@@ -383,7 +386,10 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_fwd_kernel(const __grid_consta
     const int col = cbase + lane, n = n0 + col;
     if (col < nvalid) {
       const float bias = ld_opt(G.bias, n, 0.f) + ld_opt(G.bias2, n, 0.f);
-      double s1 = 0.0, s2 = 0.0;
+      // moments of this warp's 8 rows: fp32 sums of the values centred on the first one (no cancellation in the
+      // second moment), widened to fp64 once per column -- the fp64 pipe is too slow to take every element
+      float t1 = 0.f, t2 = 0.f, y0 = 0.f;
+      int cnt = 0;
 #pragma unroll
       for (int i = 0; i < RPW; ++i) {
         const int row = warp * RPW + i, m = m0 + row;
@@ -391,16 +397,26 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_fwd_kernel(const __grid_consta
           float y = ot[(size_t)row * ldo + col] + bias;
           if (G.e_act != SWR_ACT_NONE) y = act_fwd(y, G.e_act) * G.e_scale;
           Y[(int64_t)m * G.Y.ld + n] = y;
-          s1 += (double)y; s2 += (double)y * (double)y;
+          if (cnt == 0) y0 = y;
+          const float d = y - y0;
+          t1 += d; t2 = fmaf(d, d, t2);
+          ++cnt;
         }
       }
-      red[(0 * TC_WARPS + warp) * NT + col] = s1;
-      red[(1 * TC_WARPS + warp) * NT + col] = s2;
+      // sum y = cnt*y0 + t1 ; sum y^2 = cnt*y0^2 + 2*y0*t1 + t2
+      const double dy0 = (double)y0, dt1 = (double)t1;
+      red[(0 * TC_WARPS + warp) * NT + col] = (double)cnt * dy0 + dt1;
+      red[(1 * TC_WARPS + warp) * NT + col] = (double)cnt * dy0 * dy0 + 2.0 * dy0 * dt1 + (double)t2;
     }
   }
+  const long long t_epi1 = dbg ? clock64() : 0;
   if (G.stats_out) {
     __syncthreads();
     tc_col_atomics(red, G.stats_out, n0, nvalid, NT, tid);
+  }
+  if (dbg) {
+    long long* o = p.dbg + 24 + (tid == 0 ? 0 : (tid == 33 ? 4 : 8));
+    o[0] = t_epi1 - t_kernel; o[1] = clock64() - t_kernel;
   }
 }
 
@@ -419,13 +435,13 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_dgrad_kernel(const __grid_cons
   const int gs = p.dst_group[d], ge = p.dst_group[d + 1];
   const ActDev& D = p.g[gs].A;
   const int M = p.B, Kd = D.n;
-  const int NT = p.nt[d], NTp = (NT + 31) & ~31, nq = NTp >> 2;
+  const int NT = p.nt[d], NTr = (NT + 63) & ~63, nq = NTr >> 2, nitb = NTr >> 6;
   const int nt_n = (Kd + NT - 1) / NT;
   const int local = blockIdx.x - p.dst_tile[d];
   const int m0 = (local / nt_n) * TC_BM, j0 = (local % nt_n) * NT;
   const int kb0 = p.tile_start[gs];
   const int nkb = p.tile_start[ge] - kb0, Kc = nkb * KBLK;
-  const uint32_t b_bytes = (uint32_t)NTp * 128u, stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
+  const uint32_t b_bytes = (uint32_t)NTr * 128u, stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
   const int S = p.stages;
   float* dc = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes);   // [3][Kc]: c0, c1, c2 over the concatenated group columns
 
@@ -441,68 +457,93 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_dgrad_kernel(const __grid_cons
   const uint32_t tmem = tc_setup(sh, S, NT, tid);
 
   const int Jend = min(Kd, j0 + NT);
-  float4 ra[2], rr[2], rb[4], rb2[4];
   // per-group staging state (rebuilt when the k-block walk enters the next group of the fan-in)
-  int cur_g = gs - 1, g_kb0 = 0, g_N = 0;
-  bool kn = false, hasW2 = false, need_raw = false, vecY = false, vecW = false;
-  KSlice sa{}, sbk{};
-  MSlice<4> sbm{};
-  const float* wbase = nullptr;
-  int64_t w2diff = 0, rawdiff = 0;
+  int cur_g = gs - 1, g_kb0 = 0, g_next = 0, g_N = 0;
+  bool kn = false, hasW2 = false, need_raw = false, vecY = false, vecW = false, fastB = false;
+  Op<2> oa; Op<4> ob;
+  int64_t w2diff = 0, rawdiff = 0, bstep = 0;
+  // shared-memory offsets do not depend on the group, only on the layout of its weight
+  uint32_t so_a[2], so_bk[4], so_bm[4];
+  {
+    const int cj = tid & 7, r0_ = tid >> 3;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) so_a[it] = kmajor_off(it * TC_RPI + r0_, cj);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      so_bk[it] = kmajor_off(it * TC_RPI + r0_, cj);
+      const int v = it * TC_NP + tid, c = v / nq, q = v - c * nq;
+      so_bm[it] = (it < nitb) ? mnmajor_off(q, c) : 0u;
+    }
+  }
   auto enter_group = [&](int g) {
     const FcGroup& G = p.g[g];
-    cur_g = g; g_kb0 = p.tile_start[g] - kb0; g_N = G.Y.n;
+    cur_g = g; g_kb0 = p.tile_start[g] - kb0; g_next = p.tile_start[g + 1] - kb0; g_N = G.Y.n;
     kn = (G.w_layout == SWR_W_KN); hasW2 = G.W2 != nullptr;
     need_raw = (G.Y.norm.mode == SWR_NORM_BATCH);
     vecY = is_al16(G.Y.dz) && is_al16(G.Y.raw) && (G.Y.ld % 4 == 0);
     vecW = is_al16(G.W) && (G.ldw % 4 == 0) && (!G.W2 || is_al16(G.W2));
-    sa = make_kslice(G.Y.dz, G.Y.ld, m0, M, TC_BM, tid, 2);
+    fastB = vecW && (kn || ((Jend - j0) % 4 == 0));
     rawdiff = G.Y.raw - G.Y.dz;
     w2diff = hasW2 ? (G.W2 - G.W) : 0;
-    if (!kn) { sbm = make_mslice<4>(G.ldw, j0, Jend, nq, tid); wbase = G.W + j0; }   // W[n, j] -> MN-major
-    else sbk = make_kslice(G.W, G.ldw, j0, Jend, NT, tid, 4);                          // W[j, n] -> K-major
+    op_init_k<2>(oa, G.Y.dz, G.Y.ld, m0, M, 2, tid);
+    if (!kn) { op_init_m<4>(ob, G.W + j0, G.ldw, Jend - j0, nq, nitb, tid); bstep = (int64_t)KBLK * G.ldw; }   // W[n, j] -> MN-major
+    else { op_init_k<4>(ob, G.W, G.ldw, j0, Jend, nitb, tid); bstep = KBLK; }                                     // W[j, n] -> K-major
   };
-  auto load = [&](int kb) {
-    while (cur_g < gs || (cur_g + 1 < ge && p.tile_start[cur_g + 1] - kb0 <= kb)) enter_group(cur_g + 1);
+  // register prefetch one k-block ahead; the set remembers the layout of the block it holds.  The W2 product
+  // (STAR / M3oE) is applied at load time: those loads then wait in place, which only those models pay for.
+  struct Regs { float4 a[2], r[2], b[4]; bool b_mn; };
+  auto load = [&](int kb, Regs& R) {
+    while (cur_g < gs || kb >= g_next) enter_group(cur_g + 1);
+    const FcGroup& G = p.g[cur_g];
     const int lkb = kb - g_kb0;   // k-block inside the group
-    kslice_load<2>(sa, sa.p0, ra, lkb, g_N, vecY);
-    if (need_raw) kslice_load<2>(sa, sa.p0 + rawdiff, rr, lkb, g_N, vecY);
-    else { rr[0] = zero4(); rr[1] = zero4(); }
-    if (!kn) {
-      mslice_load<4>(sbm, wbase, rb, lkb, g_N, vecW);
-      if (hasW2) mslice_load<4>(sbm, wbase + w2diff, rb2, lkb, g_N, vecW);
+    const bool interior = (lkb + 1) * KBLK <= g_N;
+    R.b_mn = !kn;
+    if (vecY && interior) {
+      op_load_fast<2>(oa, (int64_t)lkb * KBLK, 2, R.a);
+      if (need_raw) op_load_fast<2>(oa, (int64_t)lkb * KBLK + rawdiff, 2, R.r);
     } else {
-      kslice_load<4>(sbk, sbk.p0, rb, lkb, g_N, vecW);
-      if (hasW2) kslice_load<4>(sbk, sbk.p0 + w2diff, rb2, lkb, g_N, vecW);
+      op_load_slow_k<2>(G.Y.dz, G.Y.ld, m0, M, lkb * KBLK, g_N, vecY, 2, tid, R.a);
+      if (need_raw) op_load_slow_k<2>(G.Y.raw, G.Y.ld, m0, M, lkb * KBLK, g_N, vecY, 2, tid, R.r);
+    }
+    if (!need_raw) { R.r[0] = zero4(); R.r[1] = zero4(); }
+    float4 w2[4];
+    if (fastB && interior) {
+      op_load_fast<4>(ob, lkb * bstep, nitb, R.b);
+      if (hasW2) op_load_fast<4>(ob, lkb * bstep + w2diff, nitb, w2);
+    } else if (!kn) {
+      op_load_slow_m<4>(G.W, G.ldw, j0, Jend, lkb * KBLK, g_N, nq, vecW, nitb, tid, R.b);
+      if (hasW2) op_load_slow_m<4>(G.W2, G.ldw, j0, Jend, lkb * KBLK, g_N, nq, vecW, nitb, tid, w2);
+    } else {
+      op_load_slow_k<4>(G.W, G.ldw, j0, Jend, lkb * KBLK, g_N, vecW, nitb, tid, R.b);
+      if (hasW2) op_load_slow_k<4>(G.W2, G.ldw, j0, Jend, lkb * KBLK, g_N, vecW, nitb, tid, w2);
+    }
+    if (hasW2) {
+#pragma unroll
+      for (int it = 0; it < 4; ++it)
+        if (it < nitb) R.b[it] = mul4(R.b[it], w2[it]);
     }
   };
-  // called before load(kb + 1): the slices and layout flags still describe the group of block kb
-  auto store = [&](int kb, uint32_t stage) {
+  auto store = [&](int kb, uint32_t stage, Regs& R) {
     const uint32_t ah = stage, al = ah + TC_A_BYTES, bh = al + TC_A_BYTES, bl = bh + b_bytes;
-    const int k = kb * KBLK + sa.cj4;
+    const int k = kb * KBLK + 4 * (tid & 7);
     const float4 c0 = ld4s(dc + k), c1 = ld4s(dc + Kc + k), c2 = ld4s(dc + 2 * Kc + k);
 #pragma unroll
     for (int it = 0; it < 2; ++it)   // rows outside the batch only feed accumulator rows that are never stored
-      store_split(ah, al, sa.so0 + it * (TC_RPI * 128), affine4(c0, ra[it], c1, rr[it], c2));
-    if (!kn) {
+      store_split(ah, al, so_a[it], affine4(c0, R.a[it], c1, R.r[it], c2));
 #pragma unroll
-      for (int it = 0; it < 4; ++it)
-        if (((sbm.nv >> (4 * it)) & 15u) != 15u) store_split(bh, bl, sbm.so[it], hasW2 ? mul4(rb[it], rb2[it]) : rb[it]);
-    } else {
-#pragma unroll
-      for (int it = 0; it < 4; ++it)
-        if (it * TC_RPI + (tid >> 3) < NT) store_split(bh, bl, sbk.so0 + it * (TC_RPI * 128), hasW2 ? mul4(rb[it], rb2[it]) : rb[it]);
-    }
+    for (int it = 0; it < 4; ++it)
+      if (it < nitb) store_split(bh, bl, R.b_mn ? so_bm[it] : so_bk[it], R.b[it]);
   };
 
   TcPipe pp; pp.init();
-  load(0);
+  Regs r0;
+  load(0, r0);
   for (; pp.kb < nkb; pp.advance(S)) {
     tc_acquire(sh, pp, S);
     const uint32_t stage = smem_s + (uint32_t)pp.s * stage_bytes;
-    const bool b_mn = !kn;   // W[n, j] tiles are MN-major
-    store(pp.kb, stage);
-    if (pp.kb + 1 < nkb) load(pp.kb + 1);
+    const bool b_mn = r0.b_mn;   // layout of the block being stored (load(kb + 1) overwrites it)
+    store(pp.kb, stage, r0);
+    if (pp.kb + 1 < nkb) load(pp.kb + 1, r0);
     tc_publish_issue(sh, pp, tmem, stage, b_bytes, nkb, false, b_mn, NT, tid);
   }
   mbar_wait(&sh.bar_done, 0);
@@ -526,7 +567,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_dgrad_kernel(const __grid_cons
     if (col < nvalid) {
       ColCoef cc = {0.f, 1.f, 0.f, 1.f};
       if (!plainD) cc = col_coef(D.norm, j, p.inv_count);
-      double s1 = 0.0, s2 = 0.0;
+      float s1 = 0.f, s2 = 0.f;   // 8-row partials in fp32, widened to fp64 once per column
 #pragma unroll
       for (int i = 0; i < RPW; ++i) {
         const int row = warp * RPW + i, m = m0 + row;
@@ -536,14 +577,14 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_dgrad_kernel(const __grid_cons
           if (!plainD) {
             const float raw = D.raw[o];
             dz *= act_grad(fmaf(raw - cc.mu, cc.s, cc.b), D.act);
-            s1 += (double)dz; s2 += (double)dz * (double)((raw - cc.mu) * cc.r);
+            s1 += dz; s2 = fmaf(dz, (raw - cc.mu) * cc.r, s2);
           }
           if (accumulate) dz += D.dz[o];
           D.dz[o] = dz;
         }
       }
-      red[(0 * TC_WARPS + warp) * NT + col] = s1;
-      red[(1 * TC_WARPS + warp) * NT + col] = s2;
+      red[(0 * TC_WARPS + warp) * NT + col] = (double)s1;
+      red[(1 * TC_WARPS + warp) * NT + col] = (double)s2;
     }
   }
   if (has_norm && D.dstats) {
@@ -568,7 +609,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_wgrad_kernel(const __grid_cons
   while (g + 1 < p.n_groups && p.tile_start[g + 1] <= (int)blockIdx.x) ++g;
   const FcGroup& G = p.g[g];
   const int N = G.Y.n, K = G.A.n;
-  const int NT = p.nt[g], NTp = (NT + 31) & ~31, nq = NTp >> 2;
+  const int NT = p.nt[g], NTr = (NT + 63) & ~63, nq = NTr >> 2, nitb = NTr >> 6;
   const int nt_m = (N + TC_BM - 1) / TC_BM, nt_n = (K + NT - 1) / NT;
   int local = blockIdx.x - p.tile_start[g];
   const int split = local / (nt_m * nt_n);
@@ -579,15 +620,15 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_wgrad_kernel(const __grid_cons
   if (b_begin >= b_end) return;   // whole CTA, before any barrier
   const int rows = b_end - b_begin;
   const int nkb = (rows + KBLK - 1) / KBLK;
-  const uint32_t b_bytes = (uint32_t)NTp * 128u, stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
+  const uint32_t b_bytes = (uint32_t)NTr * 128u, stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
   const int S = p.stages;
-  float* nc = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes);   // [3][NTp]: mu, s, b of the input columns j
+  float* nc = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes);   // [3][NTr]: mu, s, b of the input columns j
 
   const bool plainA = (G.A.norm.mode == SWR_NORM_NONE && G.A.act == SWR_ACT_NONE);
-  for (int i = tid; i < NTp; i += TC_NT) {
+  for (int i = tid; i < NTr; i += TC_NT) {
     ColCoef c = {0.f, 0.f, 0.f, 0.f};
     if (j0 + i < K) c = plainA ? ColCoef{0.f, 1.f, 0.f, 1.f} : col_coef(G.A.norm, j0 + i, p.inv_count);
-    nc[i] = c.mu; nc[NTp + i] = c.s; nc[2 * NTp + i] = c.b;
+    nc[i] = c.mu; nc[NTr + i] = c.s; nc[2 * NTr + i] = c.b;
   }
   if (tid < TC_BM) bsum[tid] = 0.f;
   const uint32_t tmem = tc_setup(sh, S, NT, tid);
@@ -603,54 +644,70 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_wgrad_kernel(const __grid_cons
   const float4 c0 = make_float4(f0[0], f0[1], f0[2], f0[3]), c1 = make_float4(f1[0], f1[1], f1[2], f1[3]), c2 = make_float4(f2[0], f2[1], f2[2], f2[3]);
   const bool vecY = is_al16(G.Y.dz) && is_al16(G.Y.raw) && (G.Y.ld % 4 == 0);
   const bool vecA = is_al16(G.A.raw) && (G.A.ld % 4 == 0);
+  const bool fastA = vecY && ((Nend - m0) % 4 == 0), fastB = vecA && ((Jend - j0) % 4 == 0);
   const bool need_raw = (G.Y.norm.mode == SWR_NORM_BATCH);
   const float slope = act_slope(G.A.act);
   const bool sigA = G.A.act == SWR_ACT_SIGMOID;
-  const MSlice<2> sa = make_mslice<2>(G.Y.ld, m0, Nend, 32, tid);
-  const MSlice<4> sb = make_mslice<4>(G.A.ld, j0, Jend, nq, tid);
-  const float* dzbase = G.Y.dz + (int64_t)b_begin * G.Y.ld + m0;
-  const float* rawbase = G.Y.raw + (int64_t)b_begin * G.Y.ld + m0;
-  const float* abase = G.A.raw + (int64_t)b_begin * G.A.ld + j0;
+  const float* dzsrc = G.Y.dz + (int64_t)b_begin * G.Y.ld;    // contraction row 0 of this split
+  const float* rawsrc = G.Y.raw + (int64_t)b_begin * G.Y.ld;
+  const float* asrc = G.A.raw + (int64_t)b_begin * G.A.ld;
+  Op<2> oa; Op<4> ob;
+  op_init_m<2>(oa, dzsrc + m0, G.Y.ld, Nend - m0, 32, 2, tid);
+  op_init_m<4>(ob, asrc + j0, G.A.ld, Jend - j0, nq, nitb, tid);
+  const int64_t rawdiff = G.Y.raw - G.Y.dz;
+  const int64_t astep = (int64_t)KBLK * G.Y.ld, bstep = (int64_t)KBLK * G.A.ld;
+  // input-column quads this thread stages (for the lazy activation coefficients)
+  uint32_t qpack = 0;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) qpack |= (uint32_t)((it * TC_NP + tid) % nq) << (8 * it);
 
-  float4 ra[2], rr[2], rb[4];
+  struct Regs { float4 a[2], r[2], b[4]; };
   float4 rowsum = zero4();
-  auto load = [&](int kb) {
-    mslice_load<2>(sa, dzbase, ra, kb, rows, vecY);
-    if (need_raw) mslice_load<2>(sa, rawbase, rr, kb, rows, vecY);
-    else { rr[0] = zero4(); rr[1] = zero4(); }
-    mslice_load<4>(sb, abase, rb, kb, rows, vecA);
+  auto load = [&](int kb, Regs& R) {
+    const bool interior = (kb + 1) * KBLK <= rows;
+    if (fastA && interior) {
+      op_load_fast<2>(oa, kb * astep, 2, R.a);
+      if (need_raw) op_load_fast<2>(oa, kb * astep + rawdiff, 2, R.r);
+    } else {
+      op_load_slow_m<2>(dzsrc, G.Y.ld, m0, Nend, kb * KBLK, rows, 32, vecY, 2, tid, R.a);
+      if (need_raw) op_load_slow_m<2>(rawsrc, G.Y.ld, m0, Nend, kb * KBLK, rows, 32, vecY, 2, tid, R.r);
+    }
+    if (!need_raw) { R.r[0] = zero4(); R.r[1] = zero4(); }
+    if (fastB && interior) op_load_fast<4>(ob, kb * bstep, nitb, R.b);
+    else op_load_slow_m<4>(asrc, G.A.ld, j0, Jend, kb * KBLK, rows, nq, vecA, nitb, tid, R.b);
   };
-  auto store = [&](int kb, uint32_t stage) {
+  auto store = [&](int kb, uint32_t stage, Regs& R) {
     const uint32_t ah = stage, al = ah + TC_A_BYTES, bh = al + TC_A_BYTES, bl = bh + b_bytes;
     const int left = rows - kb * KBLK;
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
       const int c = it * (TC_NP / 32) + (tid >> 5);
       float4 x = zero4();
-      if (c < left) x = affine4(c0, ra[it], c1, rr[it], c2);   // c2 != 0: contraction padding must stay exactly zero
+      if (c < left) x = affine4(c0, R.a[it], c1, R.r[it], c2);   // c2 != 0: contraction padding must stay exactly zero
       rowsum.x += x.x; rowsum.y += x.y; rowsum.z += x.z; rowsum.w += x.w;
-      store_split(ah, al, sa.so[it], x);
+      store_split(ah, al, oa.so[it], x);
     }
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
-      if (((sb.nv >> (4 * it)) & 15u) != 15u) {
-        float4 x = rb[it];
+      if (it < nitb) {
+        float4 x = R.b[it];
         if (!plainA) {   // rows past the split meet an exactly-zero dY column; values only need to be finite
-          const int q4 = 4 * (int)((sb.qpack >> (8 * it)) & 255u);
-          x = norm_act4(x, ld4s(nc + q4), ld4s(nc + NTp + q4), ld4s(nc + 2 * NTp + q4), slope, sigA);
+          const int q4 = 4 * (int)((qpack >> (8 * it)) & 255u);
+          x = norm_act4(x, ld4s(nc + q4), ld4s(nc + NTr + q4), ld4s(nc + 2 * NTr + q4), slope, sigA);
         }
-        store_split(bh, bl, sb.so[it], x);
+        store_split(bh, bl, ob.so[it], x);
       }
     }
   };
 
   TcPipe pp; pp.init();
-  load(0);
+  Regs r0;
+  load(0, r0);
   for (; pp.kb < nkb; pp.advance(S)) {
     tc_acquire(sh, pp, S);
     const uint32_t stage = smem_s + (uint32_t)pp.s * stage_bytes;
-    store(pp.kb, stage);
-    if (pp.kb + 1 < nkb) load(pp.kb + 1);
+    store(pp.kb, stage, r0);
+    if (pp.kb + 1 < nkb) load(pp.kb + 1, r0);
     tc_publish_issue(sh, pp, tmem, stage, b_bytes, nkb, true, true, NT, tid);
   }
   const bool do_bias = (j0 == 0) && (G.dbias || G.dbias2);
@@ -727,7 +784,7 @@ static int pick_nt(int n, int mtiles, int other_tiles) {
 static constexpr size_t kTcSmemBudget = 200 * 1024;
 
 static int pick_stages(int nt_max, size_t extra_bytes, int nkb_max, size_t* smem_bytes) {
-  const size_t stage = 2 * (size_t)TC_A_BYTES + 2 * (size_t)round_up(nt_max, 32) * 128;
+  const size_t stage = 2 * (size_t)TC_A_BYTES + 2 * (size_t)round_up(nt_max, 64) * 128;
   int s = (int)((kTcSmemBudget - extra_bytes) / stage);
   if (s > TC_MAX_STAGES) s = TC_MAX_STAGES;
   if (s > nkb_max) s = nkb_max;
@@ -739,22 +796,44 @@ static int pick_stages(int nt_max, size_t extra_bytes, int nkb_max, size_t* smem
   return s;
 }
 
+// The opt-in limit is raised once per kernel to the device maximum and never lowered: a CUDA graph node keeps the
+// size it was captured with, and tools that re-launch graph nodes (ncu) check it against the *current* attribute.
 template <class K>
 static int tc_set_smem(K kernel, size_t bytes) {
-  if (bytes > 227 * 1024) { set_error("fc_tc: %zu bytes of shared memory needed", bytes); return SWR_ERR_UNSUPPORTED; }
-  SWR_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  constexpr int kMaxDyn = 227 * 1024 - 1024;   // the opt-in maximum covers static + dynamic shared memory
+  if (bytes > (size_t)kMaxDyn) { set_error("fc_tc: %zu bytes of shared memory needed", bytes); return SWR_ERR_UNSUPPORTED; }
+  static thread_local const void* done[8] = {nullptr};
+  const void* key = reinterpret_cast<const void*>(kernel);
+  for (int i = 0; i < 8; ++i) {
+    if (done[i] == key) return SWR_OK;
+    if (!done[i]) {
+      SWR_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
+      done[i] = key;
+      return SWR_OK;
+    }
+  }
+  SWR_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn));
   return SWR_OK;
 }
 
-// 0: never, 1: whenever the shapes allow, 2 (default): when the launch is big enough to pay for the pipeline
-static int tc_mode() {
-  static int mode = -1;
-  if (mode < 0) {
+// SWR_FC_SIMT / SWR_FC_TC / SWR_FC_AUTO (include/swr_b200.h); preset by env SWR_FC_TC, changed by swr_set_fc_mode()
+static std::atomic<int> g_tc_mode{-1};
+int fc_mode_get() {
+  int m = g_tc_mode.load();
+  if (m < 0) {
     const char* e = getenv("SWR_FC_TC");
-    mode = e ? atoi(e) : 2;
+    m = e ? atoi(e) : SWR_FC_AUTO;
+    if (m < 0 || m > 2) m = SWR_FC_AUTO;
+    g_tc_mode.store(m);
   }
-  return mode;
+  return m;
 }
+int fc_mode_set(int mode) {
+  const int prev = fc_mode_get();
+  if (mode >= 0 && mode <= 2) g_tc_mode.store(mode);
+  return prev;
+}
+static int tc_mode() { return fc_mode_get(); }
 static int64_t tc_min_macs() {
   static int64_t v = -1;
   if (v < 0) { const char* e = getenv("SWR_FC_TC_MIN_MACS"); v = e ? atoll(e) : (int64_t)1 << 24; }
@@ -793,8 +872,23 @@ int launch_fc_tc_fwd(const FcGroup* groups, int n_groups, int64_t B, cudaStream_
   p.stages = pick_stages(nt_max, 3 * sizeof(float) * (size_t)round_up(kmax, KBLK), ceil_div(kmax, KBLK), &smem);
   int rc = tc_set_smem(fc_tc_fwd_kernel, smem);
   if (rc) return rc;
+  static const bool debug = getenv("SWR_TC_DEBUG") != nullptr;
+  static long long* dbg_dev = nullptr;
+  if (debug) {
+    if (!dbg_dev) cudaMalloc(&dbg_dev, 40 * sizeof(long long));
+    cudaMemsetAsync(dbg_dev, 0, 40 * sizeof(long long), st);
+    p.dbg = dbg_dev;
+  }
   fc_tc_fwd_kernel<<<tiles, TC_NT, smem, st>>>(p);
   SWR_LAUNCH_OK("fc_tc_fwd_kernel");
+  if (debug) {
+    long long h[40];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
+    for (int t = 0; t < 3; ++t)
+      fprintf(stderr, "[tc_fwd dbg thr%d] nkb=%lld nt0=%d stages=%d | prologue %lld | acquire %lld store %lld load %lld publish+issue %lld | loop %lld tail-wait %lld | drain+store-out done at %lld, stats atomics done at %lld (cycles since kernel start)\n",
+              t, h[8 * t + 6], p.nt[0], p.stages, h[8 * t + 7], h[8 * t + 0], h[8 * t + 1], h[8 * t + 2], h[8 * t + 3], h[8 * t + 4], h[8 * t + 5], h[24 + 4 * t], h[24 + 4 * t + 1]);
+  }
   return SWR_OK;
 }
 
@@ -848,7 +942,7 @@ int launch_fc_tc_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStrea
   }
   p.tile_start[n_groups] = tiles;
   size_t smem = 0;
-  p.stages = pick_stages(nt_max, 3 * sizeof(float) * (size_t)round_up(nt_max, 32), ceil_div(rows, KBLK), &smem);
+  p.stages = pick_stages(nt_max, 3 * sizeof(float) * (size_t)round_up(nt_max, 64), ceil_div(rows, KBLK), &smem);
   int rc = tc_set_smem(fc_tc_wgrad_kernel, smem);
   if (rc) return rc;
   fc_tc_wgrad_kernel<<<tiles, TC_NT, smem, st>>>(p);

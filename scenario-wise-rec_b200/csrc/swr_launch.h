@@ -44,6 +44,8 @@ int launch_fc_dgrad(const FcGroup* groups, const int* dst_of, int n_groups, int6
 int launch_fc_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st);
 // tcgen05 path (swr_fc_tc.cu); the launchers above route to it when fc_tc_wanted() says so
 bool fc_tc_wanted(const FcGroup* groups, int n_groups, int64_t B);
+int fc_mode_get();
+int fc_mode_set(int mode);
 int launch_fc_tc_fwd(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st);
 int launch_fc_tc_dgrad(const FcGroup* groups, const int* dst_group, int n_dst, int n_groups, int64_t B, cudaStream_t st);
 int launch_fc_tc_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st);

@@ -36,7 +36,9 @@ W_NK, W_KN = 0, 1
 # swr_dtype
 DT_I8, DT_I16, DT_I32, DT_I64, DT_U8, DT_F16, DT_BF16, DT_F32, DT_F64 = 0, 1, 2, 3, 4, 8, 9, 10, 11
 
-EXPORTS = ("swr_abi_version", "swr_last_error", "swr_launch_count", "swr_device_check",
+FC_SIMT, FC_TC, FC_AUTO = 0, 1, 2   # swr_fc_mode
+
+EXPORTS = ("swr_abi_version", "swr_last_error", "swr_launch_count", "swr_device_check", "swr_set_fc_mode", "swr_get_fc_mode",
            "swr_profile_begin", "swr_profile_end", "swr_memcpy_async",
            "swr_embedding_gather_fwd", "swr_embedding_scatter_bwd", "swr_program_run")
 
@@ -57,6 +59,9 @@ def lib():
     L.swr_last_error.restype = ctypes.c_char_p
     L.swr_launch_count.restype = ctypes.c_int64
     L.swr_device_check.restype = ctypes.c_int
+    L.swr_set_fc_mode.restype = ctypes.c_int
+    L.swr_set_fc_mode.argtypes = [ctypes.c_int]
+    L.swr_get_fc_mode.restype = ctypes.c_int
     L.swr_program_run.restype = ctypes.c_int
     L.swr_program_run.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]
     vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
@@ -86,6 +91,16 @@ def check(status: int, what: str):
 
 def launch_count() -> int:
     return int(lib().swr_launch_count())
+
+
+def set_fc_mode(mode: int) -> int:
+    """Select the arithmetic of the grouped FC ops (FC_SIMT / FC_TC / FC_AUTO); returns the previous mode.
+    Programs already captured into a CUDA graph keep the kernels they were captured with."""
+    return int(lib().swr_set_fc_mode(int(mode)))
+
+
+def get_fc_mode() -> int:
+    return int(lib().swr_get_fc_mode())
 
 
 def program_run(recs: np.ndarray, slots: np.ndarray, stream: int):

@@ -113,14 +113,34 @@ def _oracle(model_name, cfg, x, y, state, dt):
     return out.detach(), {k: v.grad for k, v in st.items() if v.requires_grad}, bn_out
 
 
+@pytest.fixture
+def fc_mode(request):
+    prev = N.set_fc_mode(request.param)
+    yield request.param
+    N.set_fc_mode(prev)
+
+
+@pytest.mark.parametrize("fc_mode", [N.FC_SIMT, N.FC_AUTO], ids=["ffma", "tcgen05"], indirect=True)
 @pytest.mark.parametrize("case", sorted(BASELINE_CASES))
-def test_baseline_shapes_vs_oracle(case):
-    """BASELINE.json shapes.  Outputs: <= 1e-4 abs against the fp32 CPU oracle (north_star).  Gradients: judged
+def test_baseline_shapes_vs_oracle(case, fc_mode):
+    """BASELINE.json shapes, once per FC arithmetic (swr_set_fc_mode).  Outputs: <= 1e-4 abs against the fp32 CPU oracle (north_star).  Gradients: judged
     against the oracle evaluated in float64, with the fp32 CPU oracle's own distance to it as the noise floor --
     deep BatchNorm stacks amplify fp32 rounding (STAR cfg4a: the CPU reference itself is 1e-2 of max|g| away from
     float64), and a ReLU whose pre-activation lands within an ulp of 0 flips its derivative for one row (measure
     zero, seen once in 16384 rows on M3oE), which a max-norm alone cannot tell from a bug; such a tensor must
-    still agree in the relative L2 norm with a vanishing fraction of outlier elements."""
+    still agree in the relative L2 norm with a vanishing fraction of outlier elements.
+
+    tcgen05 mode (the default): operands are split 3xTF32 (~2^-21 per product) and the tensor core accumulates with
+    round-toward-zero instead of round-to-nearest: a truncation of about 1e-8 * K relative, *coherent in the sign of
+    the products* (tools/tc_probe.cu measures it).  Outputs stay inside 1e-4, but a gradient that sums many
+    same-signed per-sample terms which nearly cancel over the batch (30 % positive labels here) keeps the bias
+    while the sum shrinks: up to ~5e-3 of max|g| on such components (the fp32 CPU reference itself is 1e-3 from
+    float64 there).  Its per-element error (~1e-6 relative, ten times fp32's) also moves a few more pre-activations
+    across 0 than the fp32 paths do (measured on cfg2: rows 495, 717, 1613 of 4096, tools/debug_case.py); each
+    flipped row changes a weight gradient by that sample's own contribution, ~1/sqrt(B) of max|g|, spread over
+    the whole tensor.  The tensor-core bound is therefore max-err <= max(1e-2, 8 x fp32 noise, 2/sqrt(B)) together
+    with the same relative-L2 bound; a tiling / indexing bug is O(1) in both, and the small golden cases, the
+    buffer-by-buffer comparison against the interpreter and the 1e-4 output bound stay as tight as for FFMA."""
     model_name, cfg, B = BASELINE_CASES[case]
     torch.manual_seed(7)
     model = model_factory.build(model_name, cfg)
@@ -149,6 +169,8 @@ def test_baseline_shapes_vs_oracle(case):
         nrm = max(float(t.norm()), 1e-12)
         l2_ours, l2_ref = float((ours - t).norm()) / nrm, float((g32[k].double() - t).norm()) / nrm
         outliers = float(((ours - t).abs() > 5e-4 * scale).double().mean())
+        if fc_mode != N.FC_SIMT and e_ours <= max(1e-2, 8 * e_ref, 2.0 / B ** 0.5) and l2_ours <= max(1e-2, 4 * l2_ref):
+            continue
         # one flipped row perturbs one row / column of a weight gradient or one row of a table whose gradient
         # lives on <= B rows: rel-L2 up to ~1/sqrt(B) * O(1); a tiling / indexing bug shows up as O(1) instead
         assert l2_ours <= max(1e-2, 4 * l2_ref) and outliers <= 2e-2, \
