@@ -207,6 +207,68 @@ def op_table(recs, B, feats):
     return out
 
 
+def saturated_gather_scatter(feats, dev, pk, lookups_log2=18):
+    """K1 / K2 through the raw C ABI at a size that fills the machine (2^18 batch rows x every sparse field of the
+    workload = ~6 M lookups per launch), fresh random indices per launch, CUDA events on the launch stream."""
+    import ctypes
+    from scenario_wise_rec_b200 import _native as N
+    sp = [(v, d) for _, k, v, d in feats if k == "sparse"]
+    nd = sum(1 for _, k, _, _ in feats if k == "dense")
+    E = sp[0][1]
+    if any(d != E for _, d in sp):
+        return None
+    Bs = 1 << lookups_log2
+    g = torch.Generator(device=dev).manual_seed(17)
+    tables = [torch.randn(v, E, device=dev, generator=g) for v, _ in sp]
+    gtabs = [torch.zeros(v, E, device=dev) for v, _ in sp]
+    sets = [[torch.randint(0, v, (Bs,), device=dev, generator=g) for v, _ in sp] for _ in range(4)]
+    dense = [torch.rand(Bs, device=dev, generator=g) for _ in range(nd)]
+    IN = len(sp) * E + nd
+    out = torch.empty(Bs, IN, device=dev)
+    oob = torch.zeros(2, dtype=torch.int32, device=dev)
+    arr = lambda ts: (ctypes.c_void_p * max(len(ts), 1))(*[t.data_ptr() for t in ts])      # noqa: E731
+    vocab = (ctypes.c_int64 * len(sp))(*[v for v, _ in sp])
+    idt = (ctypes.c_int32 * len(sp))(*[N.DT_I64] * len(sp))
+    ddt = (ctypes.c_int32 * max(nd, 1))(*[N.DT_F32] * nd)
+    st = torch.cuda.current_stream().cuda_stream
+    L = N.lib()
+
+    def gather(i):
+        N.check(L.swr_embedding_gather_fwd(arr(tables), vocab, arr(sets[i % 4]), idt, arr(dense) if nd else None, ddt, out.data_ptr(),
+                                           IN, Bs, len(sp), E, nd, oob.data_ptr(), st), "gather")
+
+    def scatter(i):
+        N.check(L.swr_embedding_scatter_bwd(out.data_ptr(), IN, Bs, arr(sets[i % 4]), idt, arr(gtabs), vocab, len(sp), E, st), "scatter")
+
+    res = {}
+    for name, fn, per in (("gather", gather, workloads.gather_bytes_per_sample(feats)), ("scatter", scatter, workloads.scatter_bytes_per_sample(feats))):
+        for i in range(3):
+            fn(i)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(10):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        gbps = per * Bs / ms / 1e6
+        res[name] = {"rows": Bs, "lookups": Bs * len(sp), "ms": ms, "GBps": gbps, "frac_hbm": gbps / pk["hbm"]}
+    return res
+
+
+def ncu_traffic(op_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the op's kernel, from the committed ncu --set full
+    capture (profiles/ncu_traffic.json, written by tools/summarize_profiles.py); None if that op was not captured."""
+    f = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(f):
+        return None
+    try:
+        return json.load(open(f)).get(op_name)
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -320,7 +382,8 @@ def main():
         ach = top["work"] / (top["ms"] * 1e-3) / 1e9 if top["work"] else None
         roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": (ach / pk["hbm"]) if ach else None, "traffic": None}
     roof.update(kernel=top["op"], kernel_ms=top["ms"], peak_source=pk["source"],
-                share_of_step=top["ms"] / max(sum(o["ms"] for o in ops), 1e-9))
+                share_of_step=top["ms"] / max(sum(o["ms"] for o in ops), 1e-9), traffic=ncu_traffic(top["op"]))
+    sat = saturated_gather_scatter(feats, dev, pk) if rank == 0 else None
     gather = next((o for o in ops if o["op"] == "gather"), None)
     scatter = next((o for o in ops if o["op"] == "scatter"), None)
 
@@ -342,6 +405,8 @@ def main():
         "ops_ms_total": round(sum(o["ms"] for o in ops), 5),
         "gather": None if not gather else {"ms": gather["ms"], "GBps": gather["work"] / gather["ms"] / 1e6, "frac_hbm": gather["work"] / gather["ms"] / 1e6 / pk["hbm"]},
         "scatter": None if not scatter else {"ms": scatter["ms"], "GBps": scatter["work"] / scatter["ms"] / 1e6, "frac_hbm": scatter["work"] / scatter["ms"] / 1e6 / pk["hbm"]},
+        "gather_scatter_saturated": sat,
+        "fc_arithmetic": {0: "fp32 FFMA", 1: "tcgen05 3xTF32 (all FC layers)", 2: "tcgen05 3xTF32 (wide FC layers) + fp32 FFMA (narrow)"}[N.get_fc_mode()],
         "wall_ms_per_step": wall / args.steps,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -44,6 +44,7 @@ struct TcParams {
   int B;
   float inv_count;
   int stages;
+  int epi_off;                     // byte offset (from the aligned shared-memory base) of tables that must survive the epilogue's reuse of the stages
   int splits;                      // wgrad: batch splits
   int rows_per_split;
   long long* dbg;                  // development aid: per-phase cycle counts of CTA 0 (null in production)
@@ -454,9 +455,18 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_dgrad_kernel(const __grid_cons
       dc[base + n] = c.c0; dc[Kc + base + n] = c.c1; dc[2 * Kc + base + n] = c.c2;
     }
   }
+  // coefficients of the destination's own norm / activation for the epilogue: one column per thread, once per CTA
+  const int Jend = min(Kd, j0 + NT);
+  const bool has_norm = D.norm.mode != SWR_NORM_NONE;
+  const bool plainD = !has_norm && D.act == SWR_ACT_NONE;
+  float* ccs = reinterpret_cast<float*>(smem + p.epi_off);   // [4][NT]: mu, s, b, r
+  for (int c = tid; c < NT; c += TC_NT) {
+    ColCoef cc = {0.f, 1.f, 0.f, 1.f};
+    if (!plainD && j0 + c < Jend) cc = col_coef(D.norm, j0 + c, p.inv_count);
+    ccs[c] = cc.mu; ccs[NT + c] = cc.s; ccs[2 * NT + c] = cc.b; ccs[3 * NT + c] = cc.r;
+  }
   const uint32_t tmem = tc_setup(sh, S, NT, tid);
 
-  const int Jend = min(Kd, j0 + NT);
   // per-group staging state (rebuilt when the k-block walk enters the next group of the fan-in)
   int cur_g = gs - 1, g_kb0 = 0, g_next = 0, g_N = 0;
   bool kn = false, hasW2 = false, need_raw = false, vecY = false, vecW = false, fastB = false;
@@ -558,15 +568,12 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_dgrad_kernel(const __grid_cons
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, tmem_cols(NT));
   const bool accumulate = (p.g[gs].flags & FC_A_ACCUMULATE) != 0;
-  const bool has_norm = D.norm.mode != SWR_NORM_NONE;
-  const bool plainD = !has_norm && D.act == SWR_ACT_NONE;
   const int nvalid = Jend - j0;
   constexpr int RPW = TC_BM / TC_WARPS;
   for (int cbase = 0; cbase < nvalid; cbase += 32) {
     const int col = cbase + lane, j = j0 + col;
     if (col < nvalid) {
-      ColCoef cc = {0.f, 1.f, 0.f, 1.f};
-      if (!plainD) cc = col_coef(D.norm, j, p.inv_count);
+      const ColCoef cc = {ccs[col], ccs[NT + col], ccs[2 * NT + col], ccs[3 * NT + col]};
       float s1 = 0.f, s2 = 0.f;   // 8-row partials in fp32, widened to fp64 once per column
 #pragma unroll
       for (int i = 0; i < RPW; ++i) {
@@ -630,18 +637,20 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_wgrad_kernel(const __grid_cons
     if (j0 + i < K) c = plainA ? ColCoef{0.f, 1.f, 0.f, 1.f} : col_coef(G.A.norm, j0 + i, p.inv_count);
     nc[i] = c.mu; nc[NTr + i] = c.s; nc[2 * NTr + i] = c.b;
   }
-  if (tid < TC_BM) bsum[tid] = 0.f;
+  float* mcs = nc + 3 * NTr;   // [3][128]: c0, c1, c2 of the dY rows (output features) of this tile
+  if (tid < TC_BM) {
+    bsum[tid] = 0.f;
+    DyCoef c = {0.f, 0.f, 0.f};
+    if (m0 + tid < N) c = dy_coef(G.Y, m0 + tid, p.inv_count);
+    mcs[tid] = c.c0; mcs[TC_BM + tid] = c.c1; mcs[2 * TC_BM + tid] = c.c2;
+  }
   const uint32_t tmem = tc_setup(sh, S, NT, tid);
 
   // A(n, b) = dY[b, n]: n-contiguous -> MN-major tile; this thread always stages the same 4 output features
   // (quad aq of contraction rows it*16 + tid/32), so their dY coefficients live in registers
   const int aq = tid & 31;
   const int Nend = min(N, m0 + TC_BM), Jend = min(K, j0 + NT);
-  float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    if (m0 + 4 * aq + i < N) { const DyCoef c = dy_coef(G.Y, m0 + 4 * aq + i, p.inv_count); f0[i] = c.c0; f1[i] = c.c1; f2[i] = c.c2; }
-  const float4 c0 = make_float4(f0[0], f0[1], f0[2], f0[3]), c1 = make_float4(f1[0], f1[1], f1[2], f1[3]), c2 = make_float4(f2[0], f2[1], f2[2], f2[3]);
+  const float4 c0 = ld4s(mcs + 4 * aq), c1 = ld4s(mcs + TC_BM + 4 * aq), c2 = ld4s(mcs + 2 * TC_BM + 4 * aq);
   const bool vecY = is_al16(G.Y.dz) && is_al16(G.Y.raw) && (G.Y.ld % 4 == 0);
   const bool vecA = is_al16(G.A.raw) && (G.A.ld % 4 == 0);
   const bool fastA = vecY && ((Nend - m0) % 4 == 0), fastB = vecA && ((Jend - j0) % 4 == 0);
@@ -783,16 +792,20 @@ static int pick_nt(int n, int mtiles, int other_tiles) {
 
 static constexpr size_t kTcSmemBudget = 200 * 1024;
 
-static int pick_stages(int nt_max, size_t extra_bytes, int nkb_max, size_t* smem_bytes) {
+// extra_bytes: tables behind the stages (dead once the main loop ends); keep_bytes: tables the epilogue still reads,
+// placed at *epi_off behind both the stages (+ extra) and the epilogue's output tile + reduction scratch
+static int pick_stages(int nt_max, size_t extra_bytes, int nkb_max, size_t* smem_bytes, size_t keep_bytes = 0, int* epi_off = nullptr) {
   const size_t stage = 2 * (size_t)TC_A_BYTES + 2 * (size_t)round_up(nt_max, 64) * 128;
-  int s = (int)((kTcSmemBudget - extra_bytes) / stage);
+  int s = (int)((kTcSmemBudget - extra_bytes - keep_bytes) / stage);
   if (s > TC_MAX_STAGES) s = TC_MAX_STAGES;
   if (s > nkb_max) s = nkb_max;
   if (s < 2) s = 2;
   size_t need = (size_t)s * stage + extra_bytes;
   const size_t epi = (size_t)TC_BM * (nt_max + 4) * sizeof(float) + 2 * (size_t)TC_WARPS * nt_max * sizeof(double);   // ot + red
   if (epi > need) need = epi;
-  *smem_bytes = 1024 + need;
+  need = (need + 15) & ~(size_t)15;
+  if (epi_off) *epi_off = (int)need;
+  *smem_bytes = 1024 + need + keep_bytes;
   return s;
 }
 
@@ -912,7 +925,7 @@ int launch_fc_tc_dgrad(const FcGroup* groups, const int* dst_group, int n_dst, i
   }
   p.dst_tile[n_dst] = tiles;
   size_t smem = 0;
-  p.stages = pick_stages(nt_max, 3 * sizeof(float) * (size_t)nkb_max * KBLK, nkb_max, &smem);
+  p.stages = pick_stages(nt_max, 3 * sizeof(float) * (size_t)nkb_max * KBLK, nkb_max, &smem, 4 * sizeof(float) * (size_t)nt_max, &p.epi_off);
   int rc = tc_set_smem(fc_tc_dgrad_kernel, smem);
   if (rc) return rc;
   fc_tc_dgrad_kernel<<<tiles, TC_NT, smem, st>>>(p);
@@ -942,7 +955,7 @@ int launch_fc_tc_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStrea
   }
   p.tile_start[n_groups] = tiles;
   size_t smem = 0;
-  p.stages = pick_stages(nt_max, 3 * sizeof(float) * (size_t)round_up(nt_max, 64), ceil_div(rows, KBLK), &smem);
+  p.stages = pick_stages(nt_max, 3 * sizeof(float) * ((size_t)round_up(nt_max, 64) + TC_BM), ceil_div(rows, KBLK), &smem);
   int rc = tc_set_smem(fc_tc_wgrad_kernel, smem);
   if (rc) return rc;
   fc_tc_wgrad_kernel<<<tiles, TC_NT, smem, st>>>(p);

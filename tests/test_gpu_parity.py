@@ -138,8 +138,8 @@ def test_baseline_shapes_vs_oracle(case, fc_mode):
     float64 there).  Its per-element error (~1e-6 relative, ten times fp32's) also moves a few more pre-activations
     across 0 than the fp32 paths do (measured on cfg2: rows 495, 717, 1613 of 4096, tools/debug_case.py); each
     flipped row changes a weight gradient by that sample's own contribution, ~1/sqrt(B) of max|g|, spread over
-    the whole tensor.  The tensor-core bound is therefore max-err <= max(1e-2, 8 x fp32 noise, 2/sqrt(B)) together
-    with the same relative-L2 bound; a tiling / indexing bug is O(1) in both, and the small golden cases, the
+    the whole tensor.  The tensor-core bound is therefore max-err <= max(1e-2, 8 x fp32 noise, 2/sqrt(B)) and
+    relative L2 <= max(1e-2, 4 x fp32 noise, 2/sqrt(B)); a tiling / indexing bug is O(1) in both, and the small golden cases, the
     buffer-by-buffer comparison against the interpreter and the 1e-4 output bound stay as tight as for FFMA."""
     model_name, cfg, B = BASELINE_CASES[case]
     torch.manual_seed(7)
@@ -169,7 +169,8 @@ def test_baseline_shapes_vs_oracle(case, fc_mode):
         nrm = max(float(t.norm()), 1e-12)
         l2_ours, l2_ref = float((ours - t).norm()) / nrm, float((g32[k].double() - t).norm()) / nrm
         outliers = float(((ours - t).abs() > 5e-4 * scale).double().mean())
-        if fc_mode != N.FC_SIMT and e_ours <= max(1e-2, 8 * e_ref, 2.0 / B ** 0.5) and l2_ours <= max(1e-2, 4 * l2_ref):
+        flip = 2.0 / B ** 0.5
+        if fc_mode != N.FC_SIMT and e_ours <= max(1e-2, 8 * e_ref, flip) and l2_ours <= max(1e-2, 4 * l2_ref, flip):
             continue
         # one flipped row perturbs one row / column of a weight gradient or one row of a table whose gradient
         # lives on <= B rows: rel-L2 up to ~1/sqrt(B) * O(1); a tiling / indexing bug shows up as O(1) instead
