@@ -282,6 +282,9 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
+    if os.environ.get("SWR_BENCH_WATCHDOG"):     # development aid: dump every thread's Python stack if the run stalls
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["SWR_BENCH_WATCHDOG"]), repeat=False, exit=True)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -418,7 +421,13 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # the captured step graphs hold NCCL work on the communicator: destroy_process_group() would wait on it
+        # forever.  Everybody is past the last collective once the barrier returns; leave without the teardown.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

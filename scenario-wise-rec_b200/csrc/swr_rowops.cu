@@ -207,6 +207,7 @@ int launch_pool_bwd(const PoolLaunch& l, cudaStream_t st) {
 struct HeadParams {
   HeadDomain dom[kMaxDomains];
   int n_domains, dom_dtype, sig_before_select, B;
+  int hmax;                        // widest tower hidden layer
   const void* domain_id;
   float* out; const float* gout; const float* add; float* dadd;
   int ld_add;
@@ -215,7 +216,18 @@ struct HeadParams {
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
 
+// Per-column coefficients of the lazily normalised tower activations are staged once per CTA: col_coef() is a
+// dependent chain of an L2 load and fp64 rsqrt, far too slow to repeat per row and column.
 __global__ void __launch_bounds__(kRowThreads) head_fwd_kernel(const __grid_constant__ HeadParams p) {
+  extern __shared__ __align__(16) float4 hc[];   // [n_domains][hmax]: mu, s, b, r
+  const int Hs = p.hmax;
+  for (int i = threadIdx.x; i < p.n_domains * Hs; i += blockDim.x) {
+    const int d = i / Hs, h = i - d * Hs;
+    ColCoef c = {0.f, 1.f, 0.f, 1.f};
+    if (h < p.dom[d].A.n) c = col_coef(p.dom[d].A.norm, h, p.inv_count);
+    hc[i] = make_float4(c.mu, c.s, c.b, c.r);
+  }
+  __syncthreads();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= p.B) return;
   const int64_t d = p.sig_before_select == SWR_HEAD_NO_SELECT ? 0 : load_index(p.domain_id, p.dom_dtype, b);
@@ -224,15 +236,16 @@ __global__ void __launch_bounds__(kRowThreads) head_fwd_kernel(const __grid_cons
   if (sel) {
     const HeadDomain& D = p.dom[d];
     const int H = D.A.n;
+    const float4* cd = hc + d * Hs;
     if (D.w) {
       v = ld_opt(D.bias, 0, 0.f);
       for (int h = 0; h < H; ++h) {
-        const ColCoef c = col_coef(D.A.norm, h, p.inv_count);
-        v = fmaf(act_value(D.A.raw[(int64_t)b * D.A.ld + h], c, D.A.act), __ldg(D.w + h), v);
+        const float4 c = cd[h];
+        v = fmaf(act_fwd(fmaf(D.A.raw[(int64_t)b * D.A.ld + h] - c.x, c.y, c.z), D.A.act), __ldg(D.w + h), v);
       }
     } else {
-      const ColCoef c = col_coef(D.A.norm, 0, p.inv_count);
-      v = act_value(D.A.raw[(int64_t)b * D.A.ld], c, D.A.act);
+      const float4 c = cd[0];
+      v = act_fwd(fmaf(D.A.raw[(int64_t)b * D.A.ld] - c.x, c.y, c.z), D.A.act);
     }
   }
   float y;
@@ -241,14 +254,23 @@ __global__ void __launch_bounds__(kRowThreads) head_fwd_kernel(const __grid_cons
   p.out[b] = y;
 }
 
-// grid.y = domain
+// grid.y = domain.  Column sums leave the CTA as one atomic per column: warps combine in shared memory first.
 __global__ void __launch_bounds__(kRowThreads) head_bwd_kernel(const __grid_constant__ HeadParams p) {
+  extern __shared__ __align__(16) float4 hc[];   // [H] coefficients, then [H] dw (float), [H][2] stats (double)
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = b < p.B;
   const int d = blockIdx.y;
   const HeadDomain& D = p.dom[d];
   const int H = D.A.n;
+  double* sst = reinterpret_cast<double*>(hc + H);
+  float* sdw = reinterpret_cast<float*>(sst + 2 * H);
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    const ColCoef c = col_coef(D.A.norm, h, p.inv_count);
+    hc[h] = make_float4(c.mu, c.s, c.b, c.r);
+    sst[2 * h] = 0.0; sst[2 * h + 1] = 0.0; sdw[h] = 0.f;
+  }
+  __syncthreads();
   float dv = 0.f, dsig = 0.f;
   if (live) {
     const int64_t di = p.sig_before_select == SWR_HEAD_NO_SELECT ? 0 : load_index(p.domain_id, p.dom_dtype, b);
@@ -258,26 +280,32 @@ __global__ void __launch_bounds__(kRowThreads) head_bwd_kernel(const __grid_cons
     if (d == 0 && p.sig_before_select == SWR_HEAD_SIG_SELECT_ADD && p.dadd) p.dadd[(int64_t)b * p.ld_add] = dsig;
   }
   const bool stats = D.A.dstats && D.A.norm.mode != SWR_NORM_NONE;
+  const bool wgrad = D.w && D.dw;
   for (int h = 0; h < H; ++h) {
-    const ColCoef c = col_coef(D.A.norm, h, p.inv_count);
+    const float4 c = hc[h];
     float dw = 0.f; double s1 = 0.0, s2 = 0.0;
     if (live) {
       const int64_t o = (int64_t)b * D.A.ld + h;
       const float raw = D.A.raw[o];
-      const float z = fmaf(raw - c.mu, c.s, c.b);
+      const float z = fmaf(raw - c.x, c.y, c.z);
       dw = dv * act_fwd(z, D.A.act);
       const float dA = D.w ? dv * __ldg(D.w + h) : dv;
       const float dz = dA * act_grad(z, D.A.act);
       if (D.A.dz) D.A.dz[o] = dz;
-      s1 = (double)dz; s2 = (double)dz * (double)((raw - c.mu) * c.r);
+      s1 = (double)dz; s2 = (double)dz * (double)((raw - c.x) * c.w);
     }
-    if (D.w && D.dw) { dw = warp_sum(dw); if (lane == 0 && dw != 0.f) atomicAdd(D.dw + h, dw); }
+    if (wgrad) { dw = warp_sum(dw); if (lane == 0 && dw != 0.f) atomicAdd(sdw + h, dw); }
     if (stats) {
       s1 = warp_sum(s1); s2 = warp_sum(s2);
-      if (lane == 0) { atomicAdd(D.A.dstats + 2 * h, s1); atomicAdd(D.A.dstats + 2 * h + 1, s2); }
+      if (lane == 0) { atomicAdd(sst + 2 * h, s1); atomicAdd(sst + 2 * h + 1, s2); }
     }
   }
   if (D.w && D.dbias) { const float t = warp_sum(dv); if (lane == 0 && t != 0.f) atomicAdd(D.dbias, t); }
+  __syncthreads();
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    if (wgrad && sdw[h] != 0.f) atomicAdd(D.dw + h, sdw[h]);
+    if (stats) { atomicAdd(D.A.dstats + 2 * h, sst[2 * h]); atomicAdd(D.A.dstats + 2 * h + 1, sst[2 * h + 1]); }
+  }
 }
 
 static int fill_head(const HeadLaunch& l, HeadParams& p) {
@@ -286,6 +314,8 @@ static int fill_head(const HeadLaunch& l, HeadParams& p) {
   p.n_domains = l.n_domains; p.dom_dtype = l.dom_dtype; p.sig_before_select = l.sig_before_select; p.B = (int)l.B;
   p.domain_id = l.domain_id; p.out = l.out; p.gout = l.gout; p.add = l.add; p.dadd = l.dadd; p.ld_add = l.ld_add;
   p.inv_count = 1.0f / (float)l.B;
+  p.hmax = 1;
+  for (int d = 0; d < l.n_domains; ++d) p.hmax = max(p.hmax, l.dom[d].A.n);
   return SWR_OK;
 }
 
@@ -294,7 +324,7 @@ int launch_head_fwd(const HeadLaunch& l, cudaStream_t st) {
   HeadParams p{};
   int rc = fill_head(l, p);
   if (rc) return rc;
-  head_fwd_kernel<<<ceil_div(l.B, kRowThreads), kRowThreads, 0, st>>>(p);
+  head_fwd_kernel<<<ceil_div(l.B, kRowThreads), kRowThreads, sizeof(float4) * p.n_domains * p.hmax, st>>>(p);
   SWR_LAUNCH_OK("head_fwd_kernel");
   return SWR_OK;
 }
@@ -305,7 +335,7 @@ int launch_head_bwd(const HeadLaunch& l, cudaStream_t st) {
   int rc = fill_head(l, p);
   if (rc) return rc;
   dim3 grid(ceil_div(l.B, kRowThreads), l.n_domains);
-  head_bwd_kernel<<<grid, kRowThreads, 0, st>>>(p);
+  head_bwd_kernel<<<grid, kRowThreads, (sizeof(float4) + 2 * sizeof(double) + sizeof(float)) * p.hmax, st>>>(p);
   SWR_LAUNCH_OK("head_bwd_kernel");
   return SWR_OK;
 }

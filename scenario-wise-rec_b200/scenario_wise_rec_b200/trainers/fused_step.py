@@ -177,6 +177,14 @@ class FusedTrainStep:
             nbytes = self.B * torch.empty((), dtype=dt).element_size()
             self.layout[name] = (off, nbytes, _NP[dt])
             off = _align(off + nbytes)
+        # the index column of a row-sharded field is not an input of the device program (the program reads the
+        # exchanged rows through the field's virtual table), but the exchange itself needs it on the device
+        for f in prog.virtual_fields:
+            if f.name not in self.layout:
+                dt = self.dts[f.name]
+                nbytes = self.B * torch.empty((), dtype=dt).element_size()
+                self.layout[f.name] = (off, nbytes, _NP[dt])
+                off = _align(off + nbytes)
         self.y_off = off
         off = _align(off + 4 * self.B)
         self.stage_bytes = off
