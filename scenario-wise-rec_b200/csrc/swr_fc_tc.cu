@@ -51,6 +51,7 @@ struct TcParams {
   int n_dst;                       // dgrad
   int dst_group[kMaxGroups + 1];
   int dst_tile[kMaxGroups + 1];
+  unsigned dst_atomic;             // bit d: destination entry d is one of several partial fan-ins of the same activation: add atomically
 };
 
 struct TcShared {
@@ -568,6 +569,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_dgrad_kernel(const __grid_cons
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, tmem_cols(NT));
   const bool accumulate = (p.g[gs].flags & FC_A_ACCUMULATE) != 0;
+  const bool atomic_dst = (p.dst_atomic >> d) & 1u;
   const int nvalid = Jend - j0;
   constexpr int RPW = TC_BM / TC_WARPS;
   for (int cbase = 0; cbase < nvalid; cbase += 32) {
@@ -586,6 +588,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_dgrad_kernel(const __grid_cons
             dz *= act_grad(fmaf(raw - cc.mu, cc.s, cc.b), D.act);
             s1 += dz; s2 = fmaf(dz, (raw - cc.mu) * cc.r, s2);
           }
+          if (atomic_dst) { atomicAdd(D.dz + o, dz); continue; }   // plain destination split over its fan-in
           if (accumulate) dz += D.dz[o];
           D.dz[o] = dz;
         }
@@ -905,15 +908,43 @@ int launch_fc_tc_fwd(const FcGroup* groups, int n_groups, int64_t B, cudaStream_
   return SWR_OK;
 }
 
-// p.n_dst / p.dst_group prepared by the caller (launch_fc_dgrad)
-int launch_fc_tc_dgrad(const FcGroup* groups, const int* dst_group, int n_dst, int n_groups, int64_t B, cudaStream_t st) {
+// dst_group[0..n_dst]: group ranges of the destinations (prepared by launch_fc_dgrad)
+int launch_fc_tc_dgrad(const FcGroup* groups, const int* dst_group_in, int n_dst, int n_groups, int64_t B, cudaStream_t st) {
   TcParams p{};
-  p.n_groups = n_groups; p.B = (int)B; p.inv_count = 1.0f / (float)B; p.n_dst = n_dst;
+  p.n_groups = n_groups; p.B = (int)B; p.inv_count = 1.0f / (float)B;
   int kb = 0;
   for (int g = 0; g < n_groups; ++g) { p.g[g] = groups[g]; p.tile_start[g] = kb; kb += ceil_div(groups[g].Y.n, KBLK); }
   p.tile_start[n_groups] = kb;
-  for (int d = 0; d <= n_dst; ++d) p.dst_group[d] = dst_group[d];
   const int mtiles = ceil_div(B, TC_BM);
+  int dst_group[kMaxGroups + 1];
+  for (int d = 0; d <= n_dst; ++d) dst_group[d] = dst_group_in[d];
+  // A single plain destination (the embedding output: no norm, no activation, so its epilogue is a bare store) with a
+  // long fan-in is split into a few partial fan-ins that add atomically: each CTA then stages a wider column tile
+  // for a shorter contraction, and the operand rows restaged per column tile drop by about a third.
+  if (n_dst == 1 && n_groups >= 2 && kb >= 16) {
+    const ActDev& D = groups[0].A;
+    const bool plain = D.norm.mode == SWR_NORM_NONE && D.act == SWR_ACT_NONE;
+    const int ntiles_min = ceil_div(D.n, 256);
+    int chunks = min(n_groups, 148 / max(1, mtiles * ntiles_min));
+    if (plain && chunks >= 2) {
+      if (!(groups[0].flags & FC_A_ACCUMULATE))
+        SWR_CUDA_OK(cudaMemsetAsync(D.dz, 0, sizeof(float) * (size_t)B * D.ld, st));
+      int d = 0, acc = 0;
+      dst_group[0] = 0;
+      for (int g = 0; g < n_groups; ++g) {
+        acc += p.tile_start[g + 1] - p.tile_start[g];
+        const int left_groups = n_groups - 1 - g, left_chunks = chunks - 1 - d;
+        const int next = g + 1 < n_groups ? p.tile_start[g + 2] - p.tile_start[g + 1] : 0;
+        // cut where the running length is closest to an even share
+        if (left_chunks > 0 && left_groups >= left_chunks && 2 * acc * chunks + next * chunks >= 2 * kb * (d + 1)) dst_group[++d] = g + 1;
+      }
+      n_dst = d + 1;
+      dst_group[n_dst] = n_groups;
+      p.dst_atomic = (1u << n_dst) - 1u;
+    }
+  }
+  p.n_dst = n_dst;
+  for (int d = 0; d <= n_dst; ++d) p.dst_group[d] = dst_group[d];
   int tiles = 0, nkb_max = 0, nt_max = 0;
   for (int d = 0; d < n_dst; ++d) {
     const int kd = groups[dst_group[d]].A.n;
@@ -943,8 +974,9 @@ int launch_fc_tc_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStrea
     base += ceil_div(groups[g].Y.n, TC_BM) * ceil_div(groups[g].A.n, p.nt[g]);
     nt_max = max(nt_max, p.nt[g]);
   }
-  // split the batch until the grid covers the machine once; keep >= 4 k-blocks (128 rows) per split
-  int splits = max(1, min(ceil_div(148, base), ceil_div(B, 4 * KBLK)));
+  // split the batch until the grid fills the machine *without spilling into a second wave* (one CTA per SM: a
+  // 149th CTA doubles the kernel's duration); keep >= 4 k-blocks (128 rows) per split
+  int splits = max(1, min(base <= 148 ? 148 / base : 1, ceil_div(B, 4 * KBLK)));
   int rows = round_up(ceil_div(B, splits), KBLK);
   splits = ceil_div(B, rows);
   p.splits = splits; p.rows_per_split = rows;
