@@ -67,13 +67,13 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 __device__ __forceinline__ uint32_t tmem_cols(int nt) { uint32_t c = 32; while ((int)c < nt) c <<= 1; return c; }
 
 // barriers + TMEM; every thread calls it, ends with a CTA barrier
-__device__ __forceinline__ uint32_t tc_setup(TcShared& sh, int stages, int nt, int tid) {
+__device__ __forceinline__ uint32_t tc_setup(TcShared& sh, int stages, uint32_t tmem_ncols, int tid) {
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&sh.bar_full[s], TC_NP); mbar_init(&sh.bar_free[s], 1); }
     mbar_init(&sh.bar_done, 1);
     fence_mbar_init();
   }
-  if (tid < 32) tmem_alloc(&sh.tmem_base, tmem_cols(nt));
+  if (tid < 32) tmem_alloc(&sh.tmem_base, tmem_ncols);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -121,6 +121,89 @@ __device__ __forceinline__ void tc_publish_issue(TcShared& sh, const TcPipe& pp,
     mma_commit(&sh.bar_free[pp.s]);
     if (pp.kb == nkb - 1) mma_commit(&sh.bar_done);
   }
+}
+
+// first n (0..4) floats at p, the rest zero
+__device__ __noinline__ float4 ld_guard(const float* __restrict__ p, int n, bool vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n == 4 && vec) return __ldg(reinterpret_cast<const float4*>(p));
+  if (n > 0) v.x = __ldg(p);
+  if (n > 1) v.y = __ldg(p + 1);
+  if (n > 2) v.z = __ldg(p + 2);
+  if (n > 3) v.w = __ldg(p + 3);
+  return v;
+}
+// ---- TS mode (forward, dgrad): the 128-row operand lives in tensor memory --------------------------------------
+// The accumulator-row operand (activations / dY) is written by the stagers straight from registers into TMEM
+// (tcgen05.st: one operand row per thread, 8 contraction elements per store) and read by the MMA as its A
+// operand; only the weight tile goes through shared memory.  That takes the 128-row operand off the shared-memory
+// port twice (the stagers' stores and the three operand reads per k-step), which is what bounds these kernels.
+// TMEM columns: [0, 256) accumulator, [256 + 64 s, 256 + 64 s + 64) stage s of the A operand (32 hi + 32 lo).
+constexpr uint32_t TS_TMEM_COLS = 512;
+constexpr uint32_t TS_A_COL0 = 256;
+__device__ __forceinline__ void tc_issue_ts(uint32_t tmem, int s, uint32_t b_saddr, uint32_t b_bytes, bool b_mn, uint32_t idesc, bool first) {
+  const uint32_t ta = tmem + TS_A_COL0 + (uint32_t)s * 64u;
+  const uint64_t dbh0 = b_mn ? mnmajor_desc(b_saddr, 0) : kmajor_desc(b_saddr, 0);
+  const uint64_t b_lo_d = (uint64_t)(b_bytes >> 4);
+  const uint64_t b_step = b_mn ? (1024u >> 4) : ((UMMA_K * 4) >> 4);
+#pragma unroll
+  for (int ks = 0; ks < KBLK / UMMA_K; ++ks) {
+    const uint64_t dbh = dbh0 + ks * b_step;
+    mma_tf32_ts(tmem, ta + 32 + 8 * ks, dbh, idesc, (first && ks == 0) ? 0u : 1u);
+    mma_tf32_ts(tmem, ta + 8 * ks, dbh + b_lo_d, idesc, 1u);
+    mma_tf32_ts(tmem, ta + 8 * ks, dbh, idesc, 1u);
+  }
+}
+__device__ __forceinline__ void tc_publish_issue_ts(TcShared& sh, const TcPipe& pp, uint32_t tmem, uint32_t b_saddr, uint32_t b_bytes, int nkb,
+                                                    bool b_mn, int nt, int tid) {
+  tmem_st_wait();          // my tcgen05.st of the A operand have landed
+  fence_before_sync();
+  fence_proxy_async();     // my shared-memory stores of the B operand are visible to the MMA unit
+  mbar_arrive(&sh.bar_full[pp.s]);
+  if (tid == ((pp.kb & (TC_WARPS - 1)) << 5)) {
+    mbar_wait(&sh.bar_full[pp.s], pp.par);
+    fence_after_sync();
+    tc_issue_ts(tmem, pp.s, b_saddr, b_bytes, b_mn, make_idesc_tf32(TC_BM, nt, false, b_mn), pp.kb == 0);
+    mma_commit(&sh.bar_free[pp.s]);
+    if (pp.kb == nkb - 1) mma_commit(&sh.bar_done);
+  }
+}
+// This thread's share of the TMEM-resident operand: row 32*(warp%4) + lane, contraction elements [8*(warp/4), +8).
+struct TsRow {
+  const float* p;      // source pointer for k-block 0 (row clamped into the matrix)
+  uint32_t taddr;      // TMEM address of (its lane quarter, column 8*(warp/4)) inside stage 0's hi block
+  int k8;              // 8 * (warp / 4)
+  bool row_ok;
+};
+__device__ __forceinline__ TsRow make_tsrow(const float* base, int ld, int row0, int row_end, uint32_t tmem, int warp, int lane) {
+  TsRow r;
+  const int row = 32 * (warp & 3) + lane;
+  r.k8 = 8 * (warp >> 2);
+  r.row_ok = row0 + row < row_end;
+  r.p = base + (int64_t)min(row0 + row, row_end - 1) * ld + r.k8;
+  r.taddr = tmem + TS_A_COL0 + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)r.k8;
+  return r;
+}
+// the 8 contraction elements of k-block kb (offset = kb*32 relative to r.p); c_len = contraction length
+__device__ __forceinline__ void tsrow_load(const TsRow& r, const float* __restrict__ p, int kb, int c_len, bool vec, float4& x0, float4& x1) {
+  const int k = kb * KBLK + r.k8;
+  if (vec && k + 8 <= c_len) {
+    x0 = __ldg(reinterpret_cast<const float4*>(p + kb * KBLK));
+    x1 = __ldg(reinterpret_cast<const float4*>(p + kb * KBLK + 4));
+  } else {
+    int n0 = c_len - k; n0 = n0 < 0 ? 0 : (n0 > 4 ? 4 : n0);
+    int n1 = c_len - k - 4; n1 = n1 < 0 ? 0 : (n1 > 4 ? 4 : n1);
+    x0 = ld_guard(p + kb * KBLK, n0, vec);
+    x1 = ld_guard(p + kb * KBLK + 4, n1, vec);
+  }
+}
+__device__ __forceinline__ void tsrow_store(const TsRow& r, int s, float4 x0, float4 x1) {
+  float4 h0, l0, h1, l1;
+  split_tf32(x0.x, h0.x, l0.x); split_tf32(x0.y, h0.y, l0.y); split_tf32(x0.z, h0.z, l0.z); split_tf32(x0.w, h0.w, l0.w);
+  split_tf32(x1.x, h1.x, l1.x); split_tf32(x1.y, h1.y, l1.y); split_tf32(x1.z, h1.z, l1.z); split_tf32(x1.w, h1.w, l1.w);
+  const uint32_t ta = r.taddr + (uint32_t)s * 64u;
+  tmem_st8(ta, h0, h1);
+  tmem_st8(ta + 32, l0, l1);
 }
 
 // accumulator tile TMEM -> shared memory ot[128][ldo] (row = accumulator row); nt multiple of 16
@@ -208,16 +291,6 @@ __device__ __forceinline__ void op_load_fast(const Op<IT>& o, int64_t adv, int n
   for (int it = 0; it < IT; ++it)
     if (it < nit) r[it] = __ldg(reinterpret_cast<const float4*>(o.p[it] + adv));
 }
-// first n (0..4) floats at p, the rest zero
-__device__ __noinline__ float4 ld_guard(const float* __restrict__ p, int n, bool vec) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (n == 4 && vec) return __ldg(reinterpret_cast<const float4*>(p));
-  if (n > 0) v.x = __ldg(p);
-  if (n > 1) v.y = __ldg(p + 1);
-  if (n > 2) v.z = __ldg(p + 2);
-  if (n > 3) v.w = __ldg(p + 3);
-  return v;
-}
 // K-major slow path: rows [row0, row_end) x contraction [c0, c_len) of base[., ld]
 template <int IT>
 __device__ __forceinline__ void op_load_slow_k(const float* base, int ld, int row0, int row_end, int c0, int c_len, bool vec, int nit, int tid, float4 (&r)[IT]) {
@@ -283,7 +356,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_fwd_kernel(const __grid_consta
   const int local = blockIdx.x - p.tile_start[g];
   const int m0 = (local / nt_n) * TC_BM, n0 = (local % nt_n) * NT;
   const int nkb = (K + KBLK - 1) / KBLK, Kpad = nkb * KBLK;
-  const uint32_t b_bytes = (uint32_t)NTr * 128u, stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
+  const uint32_t b_bytes = (uint32_t)NTr * 128u, stage_bytes = 2 * b_bytes;   // TS mode: only the weight tile is in shared memory
   const int S = p.stages;
   float* kc = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes);   // [3][Kpad]: mu, s, b of the input columns
 
@@ -295,7 +368,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_fwd_kernel(const __grid_consta
       kc[k] = c.mu; kc[Kpad + k] = c.s; kc[2 * Kpad + k] = c.b;
     }
   }
-  const uint32_t tmem = tc_setup(sh, S, NT, tid);
+  const uint32_t tmem = tc_setup(sh, S, TS_TMEM_COLS, tid);
   const bool kn = (G.w_layout == SWR_W_KN);
 
   const int Nend = min(N, n0 + NT);
@@ -306,32 +379,30 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_fwd_kernel(const __grid_consta
   const float slope = act_slope(G.A.act);
   const bool sigA = G.A.act == SWR_ACT_SIGMOID;
   const int64_t w2diff = hasW2 ? (G.W2 - G.W) : 0;
-  Op<2> oa; Op<4> ob;
-  op_init_k<2>(oa, G.A.raw, G.A.ld, m0, M, 2, tid);
+  Op<4> ob;
+  const TsRow ta = make_tsrow(G.A.raw, G.A.ld, m0, M, tmem, warp, lane);
   if (!kn) op_init_k<4>(ob, G.W, G.ldw, n0, Nend, nitb, tid);             // W [N, K] -> K-major tile
   else op_init_m<4>(ob, G.W + n0, G.ldw, Nend - n0, nq, nitb, tid);       // W [K, N] -> MN-major tile
   const int64_t bstep = kn ? (int64_t)KBLK * G.ldw : KBLK;
 
   // register prefetch one k-block ahead; W2 (STAR / M3oE only) is read at store time
-  struct Regs { float4 a[2], b[4]; };
+  struct Regs { float4 a0, a1, b[4]; };
   auto load = [&](int kb, Regs& r) {
     const bool interior = (kb + 1) * KBLK <= K;
-    if (vecA && interior) op_load_fast<2>(oa, (int64_t)kb * KBLK, 2, r.a);
-    else op_load_slow_k<2>(G.A.raw, G.A.ld, m0, M, kb * KBLK, K, vecA, 2, tid, r.a);
+    tsrow_load(ta, ta.p, kb, K, vecA, r.a0, r.a1);
     if (fastB && interior) op_load_fast<4>(ob, kb * bstep, nitb, r.b);
     else if (!kn) op_load_slow_k<4>(G.W, G.ldw, n0, Nend, kb * KBLK, K, vecW, nitb, tid, r.b);
     else op_load_slow_m<4>(G.W, G.ldw, n0, Nend, kb * KBLK, K, nq, vecW, nitb, tid, r.b);
   };
-  auto store = [&](int kb, uint32_t stage, Regs& r) {
-    const uint32_t ah = stage, al = ah + TC_A_BYTES, bh = al + TC_A_BYTES, bl = bh + b_bytes;
+  auto store = [&](int kb, uint32_t stage, int stage_idx, Regs& r) {
+    const uint32_t bh = stage, bl = bh + b_bytes;
     if (plainA) {
-#pragma unroll
-      for (int it = 0; it < 2; ++it) store_split(ah, al, oa.so[it], r.a[it]);
+      tsrow_store(ta, stage_idx, r.a0, r.a1);
     } else {   // padded k: coefficients are 0 -> act(0) stays finite and meets a zero weight
-      const int k = kb * KBLK + 4 * (tid & 7);
-      const float4 mu = ld4s(kc + k), sc = ld4s(kc + Kpad + k), bb = ld4s(kc + 2 * Kpad + k);
-#pragma unroll
-      for (int it = 0; it < 2; ++it) store_split(ah, al, oa.so[it], norm_act4(r.a[it], mu, sc, bb, slope, sigA));
+      const int k = kb * KBLK + ta.k8;
+      const float4 x0 = norm_act4(r.a0, ld4s(kc + k), ld4s(kc + Kpad + k), ld4s(kc + 2 * Kpad + k), slope, sigA);
+      const float4 x1 = norm_act4(r.a1, ld4s(kc + k + 4), ld4s(kc + Kpad + k + 4), ld4s(kc + 2 * Kpad + k + 4), slope, sigA);
+      tsrow_store(ta, stage_idx, x0, x1);
     }
     if (hasW2) {
       float4 w2[4];
@@ -358,11 +429,11 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_fwd_kernel(const __grid_consta
     tc_acquire(sh, pp, S);
     if (dbg) { const long long t = clock64(); t_acq += t - t0; t0 = t; }
     const uint32_t stage = smem_s + (uint32_t)pp.s * stage_bytes;
-    store(pp.kb, stage, r0);
+    store(pp.kb, stage, pp.s, r0);
     if (dbg) { const long long t = clock64(); t_store += t - t0; t0 = t; }
     if (pp.kb + 1 < nkb) load(pp.kb + 1, r0);
     if (dbg) { const long long t = clock64(); t_load += t - t0; t0 = t; }
-    tc_publish_issue(sh, pp, tmem, stage, b_bytes, nkb, false, kn, NT, tid);
+    tc_publish_issue_ts(sh, pp, tmem, stage, b_bytes, nkb, kn, NT, tid);
     if (dbg) { const long long t = clock64(); t_pub += t - t0; t0 = t; }
   }
   const long long t_loop_end = dbg ? clock64() : 0;
@@ -380,7 +451,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_fwd_kernel(const __grid_consta
   tc_drain(tmem, ot, ldo, NT, warp, lane);
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, tmem_cols(NT));
+  if (warp == 0) tmem_dealloc(tmem, TS_TMEM_COLS);
   float* Y = const_cast<float*>(G.Y.raw);
   const int nvalid = Nend - n0;
   constexpr int RPW = TC_BM / TC_WARPS;   // accumulator rows per warp
@@ -443,7 +514,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_dgrad_kernel(const __grid_cons
   const int m0 = (local / nt_n) * TC_BM, j0 = (local % nt_n) * NT;
   const int kb0 = p.tile_start[gs];
   const int nkb = p.tile_start[ge] - kb0, Kc = nkb * KBLK;
-  const uint32_t b_bytes = (uint32_t)NTr * 128u, stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
+  const uint32_t b_bytes = (uint32_t)NTr * 128u, stage_bytes = 2 * b_bytes;   // TS mode: only the weight tile is in shared memory
   const int S = p.stages;
   float* dc = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes);   // [3][Kc]: c0, c1, c2 over the concatenated group columns
 
@@ -466,19 +537,17 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_dgrad_kernel(const __grid_cons
     if (!plainD && j0 + c < Jend) cc = col_coef(D.norm, j0 + c, p.inv_count);
     ccs[c] = cc.mu; ccs[NT + c] = cc.s; ccs[2 * NT + c] = cc.b; ccs[3 * NT + c] = cc.r;
   }
-  const uint32_t tmem = tc_setup(sh, S, NT, tid);
+  const uint32_t tmem = tc_setup(sh, S, TS_TMEM_COLS, tid);
 
   // per-group staging state (rebuilt when the k-block walk enters the next group of the fan-in)
   int cur_g = gs - 1, g_kb0 = 0, g_next = 0, g_N = 0;
   bool kn = false, hasW2 = false, need_raw = false, vecY = false, vecW = false, fastB = false;
-  Op<2> oa; Op<4> ob;
+  TsRow ta{}; Op<4> ob;
   int64_t w2diff = 0, rawdiff = 0, bstep = 0;
   // shared-memory offsets do not depend on the group, only on the layout of its weight
-  uint32_t so_a[2], so_bk[4], so_bm[4];
+  uint32_t so_bk[4], so_bm[4];
   {
     const int cj = tid & 7, r0_ = tid >> 3;
-#pragma unroll
-    for (int it = 0; it < 2; ++it) so_a[it] = kmajor_off(it * TC_RPI + r0_, cj);
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       so_bk[it] = kmajor_off(it * TC_RPI + r0_, cj);
@@ -496,27 +565,22 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_dgrad_kernel(const __grid_cons
     fastB = vecW && (kn || ((Jend - j0) % 4 == 0));
     rawdiff = G.Y.raw - G.Y.dz;
     w2diff = hasW2 ? (G.W2 - G.W) : 0;
-    op_init_k<2>(oa, G.Y.dz, G.Y.ld, m0, M, 2, tid);
+    ta = make_tsrow(G.Y.dz, G.Y.ld, m0, M, tmem, warp, lane);
     if (!kn) { op_init_m<4>(ob, G.W + j0, G.ldw, Jend - j0, nq, nitb, tid); bstep = (int64_t)KBLK * G.ldw; }   // W[n, j] -> MN-major
     else { op_init_k<4>(ob, G.W, G.ldw, j0, Jend, nitb, tid); bstep = KBLK; }                                     // W[j, n] -> K-major
   };
   // register prefetch one k-block ahead; the set remembers the layout of the block it holds.  The W2 product
   // (STAR / M3oE) is applied at load time: those loads then wait in place, which only those models pay for.
-  struct Regs { float4 a[2], r[2], b[4]; bool b_mn; };
+  struct Regs { float4 a0, a1, r0, r1, b[4]; bool b_mn; };
   auto load = [&](int kb, Regs& R) {
     while (cur_g < gs || kb >= g_next) enter_group(cur_g + 1);
     const FcGroup& G = p.g[cur_g];
     const int lkb = kb - g_kb0;   // k-block inside the group
     const bool interior = (lkb + 1) * KBLK <= g_N;
     R.b_mn = !kn;
-    if (vecY && interior) {
-      op_load_fast<2>(oa, (int64_t)lkb * KBLK, 2, R.a);
-      if (need_raw) op_load_fast<2>(oa, (int64_t)lkb * KBLK + rawdiff, 2, R.r);
-    } else {
-      op_load_slow_k<2>(G.Y.dz, G.Y.ld, m0, M, lkb * KBLK, g_N, vecY, 2, tid, R.a);
-      if (need_raw) op_load_slow_k<2>(G.Y.raw, G.Y.ld, m0, M, lkb * KBLK, g_N, vecY, 2, tid, R.r);
-    }
-    if (!need_raw) { R.r[0] = zero4(); R.r[1] = zero4(); }
+    tsrow_load(ta, ta.p, lkb, g_N, vecY, R.a0, R.a1);
+    if (need_raw) tsrow_load(ta, ta.p + rawdiff, lkb, g_N, vecY, R.r0, R.r1);
+    else { R.r0 = zero4(); R.r1 = zero4(); }
     float4 w2[4];
     if (fastB && interior) {
       op_load_fast<4>(ob, lkb * bstep, nitb, R.b);
@@ -534,13 +598,13 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_dgrad_kernel(const __grid_cons
         if (it < nitb) R.b[it] = mul4(R.b[it], w2[it]);
     }
   };
-  auto store = [&](int kb, uint32_t stage, Regs& R) {
-    const uint32_t ah = stage, al = ah + TC_A_BYTES, bh = al + TC_A_BYTES, bl = bh + b_bytes;
-    const int k = kb * KBLK + 4 * (tid & 7);
-    const float4 c0 = ld4s(dc + k), c1 = ld4s(dc + Kc + k), c2 = ld4s(dc + 2 * Kc + k);
-#pragma unroll
-    for (int it = 0; it < 2; ++it)   // rows outside the batch only feed accumulator rows that are never stored
-      store_split(ah, al, so_a[it], affine4(c0, R.a[it], c1, R.r[it], c2));
+  auto store = [&](int kb, uint32_t stage, int stage_idx, Regs& R) {
+    const uint32_t bh = stage, bl = bh + b_bytes;
+    const int k = kb * KBLK + ta.k8;
+    // rows outside the batch only feed accumulator rows that are never stored
+    tsrow_store(ta, stage_idx,
+                affine4(ld4s(dc + k), R.a0, ld4s(dc + Kc + k), R.r0, ld4s(dc + 2 * Kc + k)),
+                affine4(ld4s(dc + k + 4), R.a1, ld4s(dc + Kc + k + 4), R.r1, ld4s(dc + 2 * Kc + k + 4)));
 #pragma unroll
     for (int it = 0; it < 4; ++it)
       if (it < nitb) store_split(bh, bl, R.b_mn ? so_bm[it] : so_bk[it], R.b[it]);
@@ -553,9 +617,9 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_dgrad_kernel(const __grid_cons
     tc_acquire(sh, pp, S);
     const uint32_t stage = smem_s + (uint32_t)pp.s * stage_bytes;
     const bool b_mn = r0.b_mn;   // layout of the block being stored (load(kb + 1) overwrites it)
-    store(pp.kb, stage, r0);
+    store(pp.kb, stage, pp.s, r0);
     if (pp.kb + 1 < nkb) load(pp.kb + 1, r0);
-    tc_publish_issue(sh, pp, tmem, stage, b_bytes, nkb, false, b_mn, NT, tid);
+    tc_publish_issue_ts(sh, pp, tmem, stage, b_bytes, nkb, b_mn, NT, tid);
   }
   mbar_wait(&sh.bar_done, 0);
   fence_after_sync();
@@ -567,7 +631,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_dgrad_kernel(const __grid_cons
   tc_drain(tmem, ot, ldo, NT, warp, lane);
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, tmem_cols(NT));
+  if (warp == 0) tmem_dealloc(tmem, TS_TMEM_COLS);
   const bool accumulate = (p.g[gs].flags & FC_A_ACCUMULATE) != 0;
   const bool atomic_dst = (p.dst_atomic >> d) & 1u;
   const int nvalid = Jend - j0;
@@ -647,7 +711,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_wgrad_kernel(const __grid_cons
     if (m0 + tid < N) c = dy_coef(G.Y, m0 + tid, p.inv_count);
     mcs[tid] = c.c0; mcs[TC_BM + tid] = c.c1; mcs[2 * TC_BM + tid] = c.c2;
   }
-  const uint32_t tmem = tc_setup(sh, S, NT, tid);
+  const uint32_t tmem = tc_setup(sh, S, tmem_cols(NT), tid);
 
   // A(n, b) = dY[b, n]: n-contiguous -> MN-major tile; this thread always stages the same 4 output features
   // (quad aq of contraction rows it*16 + tid/32), so their dY coefficients live in registers
@@ -797,8 +861,9 @@ static constexpr size_t kTcSmemBudget = 200 * 1024;
 
 // extra_bytes: tables behind the stages (dead once the main loop ends); keep_bytes: tables the epilogue still reads,
 // placed at *epi_off behind both the stages (+ extra) and the epilogue's output tile + reduction scratch
-static int pick_stages(int nt_max, size_t extra_bytes, int nkb_max, size_t* smem_bytes, size_t keep_bytes = 0, int* epi_off = nullptr) {
-  const size_t stage = 2 * (size_t)TC_A_BYTES + 2 * (size_t)round_up(nt_max, 64) * 128;
+static int pick_stages(int nt_max, size_t extra_bytes, int nkb_max, size_t* smem_bytes, size_t keep_bytes = 0, int* epi_off = nullptr,
+                       bool a_in_smem = true) {
+  const size_t stage = (a_in_smem ? 2 * (size_t)TC_A_BYTES : 0) + 2 * (size_t)round_up(nt_max, 64) * 128;
   int s = (int)((kTcSmemBudget - extra_bytes - keep_bytes) / stage);
   if (s > TC_MAX_STAGES) s = TC_MAX_STAGES;
   if (s > nkb_max) s = nkb_max;
@@ -885,7 +950,7 @@ int launch_fc_tc_fwd(const FcGroup* groups, int n_groups, int64_t B, cudaStream_
   }
   p.tile_start[n_groups] = tiles;
   size_t smem = 0;
-  p.stages = pick_stages(nt_max, 3 * sizeof(float) * (size_t)round_up(kmax, KBLK), ceil_div(kmax, KBLK), &smem);
+  p.stages = pick_stages(nt_max, 3 * sizeof(float) * (size_t)round_up(kmax, KBLK), ceil_div(kmax, KBLK), &smem, 0, nullptr, false);
   int rc = tc_set_smem(fc_tc_fwd_kernel, smem);
   if (rc) return rc;
   static const bool debug = getenv("SWR_TC_DEBUG") != nullptr;
@@ -956,7 +1021,7 @@ int launch_fc_tc_dgrad(const FcGroup* groups, const int* dst_group_in, int n_dst
   }
   p.dst_tile[n_dst] = tiles;
   size_t smem = 0;
-  p.stages = pick_stages(nt_max, 3 * sizeof(float) * (size_t)nkb_max * KBLK, nkb_max, &smem, 4 * sizeof(float) * (size_t)nt_max, &p.epi_off);
+  p.stages = pick_stages(nt_max, 3 * sizeof(float) * (size_t)nkb_max * KBLK, nkb_max, &smem, 4 * sizeof(float) * (size_t)nt_max, &p.epi_off, false);
   int rc = tc_set_smem(fc_tc_dgrad_kernel, smem);
   if (rc) return rc;
   fc_tc_dgrad_kernel<<<tiles, TC_NT, smem, st>>>(p);

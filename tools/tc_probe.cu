@@ -13,7 +13,7 @@ using namespace swr::tc;
 
 struct ProbeParams {
   const float* A; const float* B; float* D;
-  int N, C, aMN, bMN, variant, split3, positive;
+  int N, C, aMN, bMN, variant, split3, positive, aTMEM;
 };
 
 __global__ void __launch_bounds__(256, 1) probe_kernel(ProbeParams p) {
@@ -46,6 +46,22 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(ProbeParams p) {
     if (kb >= 2) { mbar_wait(&bar_free[s], ((kb >> 1) - 1) & 1); fence_after_sync(); }
     const int c0 = kb * KBLK;
     // ---- stage A ----
+    if (p.aTMEM) {   // registers -> TMEM: warp w writes lanes 32*(w%4).., columns 8*(w/4).. of the hi block, +32 for the lo block
+      const int row = 32 * (warp & 3) + lane, cg = warp >> 2;   // 8 warps: cg = 0, 1 -> each warp does two column groups
+      for (int half = 0; half < 2; ++half) {
+        const int c8 = 8 * (cg * 2 + half);
+        const float4 x0 = *reinterpret_cast<const float4*>(p.A + (size_t)row * C + c0 + c8);
+        const float4 x1 = *reinterpret_cast<const float4*>(p.A + (size_t)row * C + c0 + c8 + 4);
+        float4 h0, l0, h1, l1;
+        split_tf32(x0.x, h0.x, l0.x); split_tf32(x0.y, h0.y, l0.y); split_tf32(x0.z, h0.z, l0.z); split_tf32(x0.w, h0.w, l0.w);
+        split_tf32(x1.x, h1.x, l1.x); split_tf32(x1.y, h1.y, l1.y); split_tf32(x1.z, h1.z, l1.z); split_tf32(x1.w, h1.w, l1.w);
+        const uint32_t ta = tmem + 256 + (uint32_t)s * 64 + ((uint32_t)(32 * (warp & 3)) << 16);
+        tmem_st8(ta + c8, h0, h1);
+        tmem_st8(ta + 32 + c8, l0, l1);
+      }
+      tmem_st_wait();
+      fence_before_sync();
+    } else
     for (int v = tid; v < 128 * 8; v += 256) {
       float4 x; uint32_t off;
       if (!p.aMN) { const int r = v >> 3, j = v & 7; x = *reinterpret_cast<const float4*>(p.A + (size_t)r * C + c0 + 4 * j); off = kmajor_off(r, j); }
@@ -70,7 +86,12 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(ProbeParams p) {
         const uint64_t dbh = p.bMN ? mnmajor_desc(bh, ks, p.variant) : kmajor_desc(bh, ks);
         const uint64_t dbl = p.bMN ? mnmajor_desc(bl, ks, p.variant) : kmajor_desc(bl, ks);
         const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
-        if (p.split3 == 2) {   // corrections in their own accumulator (columns 256..)
+        if (p.aTMEM) {
+          const uint32_t ta = tmem + 256 + (uint32_t)s * 64 + 8 * ks;
+          mma_tf32_ts(tmem, ta + 32, dbh, idesc, first);
+          mma_tf32_ts(tmem, ta, dbl, idesc, 1u);
+          mma_tf32_ts(tmem, ta, dbh, idesc, 1u);
+        } else if (p.split3 == 2) {   // corrections in their own accumulator (columns 256..)
           mma_tf32(tmem + 256, dal, dbh, idesc, first);
           mma_tf32(tmem + 256, dah, dbl, idesc, 1u);
           mma_tf32(tmem, dah, dbh, idesc, first);
@@ -121,7 +142,7 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(ProbeParams p) {
 int main(int argc, char** argv) {
   if (argc < 7) { printf("usage: tc_probe aMN bMN variant N C split3\n"); return 2; }
   ProbeParams p{};
-  p.aMN = atoi(argv[1]); p.bMN = atoi(argv[2]); p.variant = atoi(argv[3]); p.N = atoi(argv[4]); p.C = atoi(argv[5]); p.split3 = atoi(argv[6]); p.positive = argc > 7 ? atoi(argv[7]) : 0;
+  p.aMN = atoi(argv[1]); p.bMN = atoi(argv[2]); p.variant = atoi(argv[3]); p.N = atoi(argv[4]); p.C = atoi(argv[5]); p.split3 = atoi(argv[6]); p.positive = argc > 7 ? atoi(argv[7]) : 0; p.aTMEM = argc > 8 ? atoi(argv[8]) : 0;
   const int M = 128, N = p.N, C = p.C;
   std::vector<float> A((size_t)M * C), B((size_t)N * C), D((size_t)M * N, 0.f);
   srand(1234);
@@ -154,7 +175,7 @@ int main(int argc, char** argv) {
       maxerr = fmax(maxerr, fabs(acc - (double)D[(size_t)m * N + n]));
       maxref = fmax(maxref, fabs(acc));
     }
-  printf("aMN=%d bMN=%d var=%d N=%d C=%d split3=%d pos=%d : max|err| = %.3e (max|ref| = %.2f) mean signed err / mean|ref| = %.3e (cpu fp32 fma chain: %.3e) %s\n",
-         p.aMN, p.bMN, p.variant, N, C, p.split3, p.positive, maxerr, maxref, serr / sref, serr32 / sref, maxerr < (p.split3 ? 1e-6 * maxref * 4 : 5e-2) ? "OK" : "MISMATCH");
+  printf("aTMEM=%d aMN=%d bMN=%d var=%d N=%d C=%d split3=%d pos=%d : max|err| = %.3e (max|ref| = %.2f) mean signed err / mean|ref| = %.3e (cpu fp32 fma chain: %.3e) %s\n",
+         p.aTMEM, p.aMN, p.bMN, p.variant, N, C, p.split3, p.positive, maxerr, maxref, serr / sref, serr32 / sref, maxerr < (p.split3 ? 1e-6 * maxref * 4 : 5e-2) ? "OK" : "MISMATCH");
   return 0;
 }
