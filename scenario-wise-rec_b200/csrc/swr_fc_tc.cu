@@ -246,6 +246,9 @@ __device__ __forceinline__ void tc_col_atomics(const double* red, double* gstats
 __device__ __forceinline__ float4 mul4(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
 __device__ __forceinline__ float4 ld4s(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {   // one 16-byte reduction instead of four 4-byte ones
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 // ---- what one thread moves per k-block ---------------------------------------------------------------------
 // An operand tile is 32 contraction elements x R rows (R = 128 for the accumulator-row operand, NT rounded up to 64 for
@@ -455,31 +458,70 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_fwd_kernel(const __grid_consta
   float* Y = const_cast<float*>(G.Y.raw);
   const int nvalid = Nend - n0;
   constexpr int RPW = TC_BM / TC_WARPS;   // accumulator rows per warp
-  for (int cbase = 0; cbase < nvalid; cbase += 32) {
-    const int col = cbase + lane, n = n0 + col;
-    if (col < nvalid) {
-      const float bias = ld_opt(G.bias, n, 0.f) + ld_opt(G.bias2, n, 0.f);
-      // moments of this warp's 8 rows: fp32 sums of the values centred on the first one (no cancellation in the
-      // second moment), widened to fp64 once per column -- the fp64 pipe is too slow to take every element
-      float t1 = 0.f, t2 = 0.f, y0 = 0.f;
-      int cnt = 0;
+  // Moments of a warp's 8 rows: fp32 sums of the values centred on the first one (no cancellation in the second
+  // moment), widened to fp64 once per column -- the fp64 pipe is too slow to take every element.
+  const bool vec_out = (nvalid % 4 == 0) && (G.Y.ld % 4 == 0) && is_al16(Y);
+  if (vec_out) {   // 4 columns per thread: 16-byte shared-memory reads and global stores
+    for (int cbase = 0; cbase < nvalid; cbase += 128) {
+      const int col = cbase + 4 * lane, n = n0 + col;
+      if (col < nvalid) {
+        float4 bias;
+        bias.x = ld_opt(G.bias, n, 0.f) + ld_opt(G.bias2, n, 0.f); bias.y = ld_opt(G.bias, n + 1, 0.f) + ld_opt(G.bias2, n + 1, 0.f);
+        bias.z = ld_opt(G.bias, n + 2, 0.f) + ld_opt(G.bias2, n + 2, 0.f); bias.w = ld_opt(G.bias, n + 3, 0.f) + ld_opt(G.bias2, n + 3, 0.f);
+        float4 t1 = zero4(), t2 = zero4(), y0 = zero4();
+        int cnt = 0;
 #pragma unroll
-      for (int i = 0; i < RPW; ++i) {
-        const int row = warp * RPW + i, m = m0 + row;
-        if (m < M) {
-          float y = ot[(size_t)row * ldo + col] + bias;
-          if (G.e_act != SWR_ACT_NONE) y = act_fwd(y, G.e_act) * G.e_scale;
-          Y[(int64_t)m * G.Y.ld + n] = y;
-          if (cnt == 0) y0 = y;
-          const float d = y - y0;
-          t1 += d; t2 = fmaf(d, d, t2);
-          ++cnt;
+        for (int i = 0; i < RPW; ++i) {
+          const int row = warp * RPW + i, m = m0 + row;
+          if (m < M) {
+            float4 y = ld4s(ot + (size_t)row * ldo + col);
+            y.x += bias.x; y.y += bias.y; y.z += bias.z; y.w += bias.w;
+            if (G.e_act != SWR_ACT_NONE) {
+              y.x = act_fwd(y.x, G.e_act) * G.e_scale; y.y = act_fwd(y.y, G.e_act) * G.e_scale;
+              y.z = act_fwd(y.z, G.e_act) * G.e_scale; y.w = act_fwd(y.w, G.e_act) * G.e_scale;
+            }
+            *reinterpret_cast<float4*>(Y + (int64_t)m * G.Y.ld + n) = y;
+            if (cnt == 0) y0 = y;
+            const float4 d = make_float4(y.x - y0.x, y.y - y0.y, y.z - y0.z, y.w - y0.w);
+            t1.x += d.x; t1.y += d.y; t1.z += d.z; t1.w += d.w;
+            t2.x = fmaf(d.x, d.x, t2.x); t2.y = fmaf(d.y, d.y, t2.y); t2.z = fmaf(d.z, d.z, t2.z); t2.w = fmaf(d.w, d.w, t2.w);
+            ++cnt;
+          }
+        }
+        // sum y = cnt*y0 + t1 ; sum y^2 = cnt*y0^2 + 2*y0*t1 + t2
+        const float y0a[4] = {y0.x, y0.y, y0.z, y0.w}, t1a[4] = {t1.x, t1.y, t1.z, t1.w}, t2a[4] = {t2.x, t2.y, t2.z, t2.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double dy0 = (double)y0a[j], dt1 = (double)t1a[j];
+          red[(0 * TC_WARPS + warp) * NT + col + j] = (double)cnt * dy0 + dt1;
+          red[(1 * TC_WARPS + warp) * NT + col + j] = (double)cnt * dy0 * dy0 + 2.0 * dy0 * dt1 + (double)t2a[j];
         }
       }
-      // sum y = cnt*y0 + t1 ; sum y^2 = cnt*y0^2 + 2*y0*t1 + t2
-      const double dy0 = (double)y0, dt1 = (double)t1;
-      red[(0 * TC_WARPS + warp) * NT + col] = (double)cnt * dy0 + dt1;
-      red[(1 * TC_WARPS + warp) * NT + col] = (double)cnt * dy0 * dy0 + 2.0 * dy0 * dt1 + (double)t2;
+    }
+  } else {
+    for (int cbase = 0; cbase < nvalid; cbase += 32) {
+      const int col = cbase + lane, n = n0 + col;
+      if (col < nvalid) {
+        const float bias = ld_opt(G.bias, n, 0.f) + ld_opt(G.bias2, n, 0.f);
+        float t1 = 0.f, t2 = 0.f, y0 = 0.f;
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+          const int row = warp * RPW + i, m = m0 + row;
+          if (m < M) {
+            float y = ot[(size_t)row * ldo + col] + bias;
+            if (G.e_act != SWR_ACT_NONE) y = act_fwd(y, G.e_act) * G.e_scale;
+            Y[(int64_t)m * G.Y.ld + n] = y;
+            if (cnt == 0) y0 = y;
+            const float d = y - y0;
+            t1 += d; t2 = fmaf(d, d, t2);
+            ++cnt;
+          }
+        }
+        const double dy0 = (double)y0, dt1 = (double)t1;
+        red[(0 * TC_WARPS + warp) * NT + col] = (double)cnt * dy0 + dt1;
+        red[(1 * TC_WARPS + warp) * NT + col] = (double)cnt * dy0 * dy0 + 2.0 * dy0 * dt1 + (double)t2;
+      }
     }
   }
   const long long t_epi1 = dbg ? clock64() : 0;
@@ -636,29 +678,65 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_dgrad_kernel(const __grid_cons
   const bool atomic_dst = (p.dst_atomic >> d) & 1u;
   const int nvalid = Jend - j0;
   constexpr int RPW = TC_BM / TC_WARPS;
-  for (int cbase = 0; cbase < nvalid; cbase += 32) {
-    const int col = cbase + lane, j = j0 + col;
-    if (col < nvalid) {
-      const ColCoef cc = {ccs[col], ccs[NT + col], ccs[2 * NT + col], ccs[3 * NT + col]};
-      float s1 = 0.f, s2 = 0.f;   // 8-row partials in fp32, widened to fp64 once per column
+  const bool vec_out = (nvalid % 4 == 0) && (D.ld % 4 == 0) && is_al16(D.dz) && is_al16(D.raw);
+  if (vec_out) {   // 4 columns per thread: 16-byte shared-memory reads, global loads / stores / reductions
+    for (int cbase = 0; cbase < nvalid; cbase += 128) {
+      const int col = cbase + 4 * lane, j = j0 + col;
+      if (col < nvalid) {
+        const float4 mu = ld4s(ccs + col), sc = ld4s(ccs + NT + col), bb = ld4s(ccs + 2 * NT + col), rr = ld4s(ccs + 3 * NT + col);
+        float4 s1 = zero4(), s2 = zero4();
 #pragma unroll
-      for (int i = 0; i < RPW; ++i) {
-        const int row = warp * RPW + i, m = m0 + row;
-        if (m < M) {
-          const int64_t o = (int64_t)m * D.ld + j;
-          float dz = ot[(size_t)row * ldo + col];
-          if (!plainD) {
-            const float raw = D.raw[o];
-            dz *= act_grad(fmaf(raw - cc.mu, cc.s, cc.b), D.act);
-            s1 += dz; s2 = fmaf(dz, (raw - cc.mu) * cc.r, s2);
+        for (int i = 0; i < RPW; ++i) {
+          const int row = warp * RPW + i, m = m0 + row;
+          if (m < M) {
+            float* dst = D.dz + (int64_t)m * D.ld + j;
+            float4 dz = ld4s(ot + (size_t)row * ldo + col);
+            if (!plainD) {
+              const float4 raw = *reinterpret_cast<const float4*>(D.raw + (int64_t)m * D.ld + j);
+              dz.x *= act_grad(fmaf(raw.x - mu.x, sc.x, bb.x), D.act); dz.y *= act_grad(fmaf(raw.y - mu.y, sc.y, bb.y), D.act);
+              dz.z *= act_grad(fmaf(raw.z - mu.z, sc.z, bb.z), D.act); dz.w *= act_grad(fmaf(raw.w - mu.w, sc.w, bb.w), D.act);
+              s1.x += dz.x; s1.y += dz.y; s1.z += dz.z; s1.w += dz.w;
+              s2.x = fmaf(dz.x, (raw.x - mu.x) * rr.x, s2.x); s2.y = fmaf(dz.y, (raw.y - mu.y) * rr.y, s2.y);
+              s2.z = fmaf(dz.z, (raw.z - mu.z) * rr.z, s2.z); s2.w = fmaf(dz.w, (raw.w - mu.w) * rr.w, s2.w);
+            }
+            if (atomic_dst) { red_add_v4(dst, dz); continue; }   // plain destination split over its fan-in
+            if (accumulate) { const float4 o = *reinterpret_cast<const float4*>(dst); dz.x += o.x; dz.y += o.y; dz.z += o.z; dz.w += o.w; }
+            *reinterpret_cast<float4*>(dst) = dz;
           }
-          if (atomic_dst) { atomicAdd(D.dz + o, dz); continue; }   // plain destination split over its fan-in
-          if (accumulate) dz += D.dz[o];
-          D.dz[o] = dz;
+        }
+        const float s1a[4] = {s1.x, s1.y, s1.z, s1.w}, s2a[4] = {s2.x, s2.y, s2.z, s2.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          red[(0 * TC_WARPS + warp) * NT + col + jj] = (double)s1a[jj];
+          red[(1 * TC_WARPS + warp) * NT + col + jj] = (double)s2a[jj];
         }
       }
-      red[(0 * TC_WARPS + warp) * NT + col] = (double)s1;
-      red[(1 * TC_WARPS + warp) * NT + col] = (double)s2;
+    }
+  } else {
+    for (int cbase = 0; cbase < nvalid; cbase += 32) {
+      const int col = cbase + lane, j = j0 + col;
+      if (col < nvalid) {
+        const ColCoef cc = {ccs[col], ccs[NT + col], ccs[2 * NT + col], ccs[3 * NT + col]};
+        float s1 = 0.f, s2 = 0.f;   // 8-row partials in fp32, widened to fp64 once per column
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+          const int row = warp * RPW + i, m = m0 + row;
+          if (m < M) {
+            const int64_t o = (int64_t)m * D.ld + j;
+            float dz = ot[(size_t)row * ldo + col];
+            if (!plainD) {
+              const float raw = D.raw[o];
+              dz *= act_grad(fmaf(raw - cc.mu, cc.s, cc.b), D.act);
+              s1 += dz; s2 = fmaf(dz, (raw - cc.mu) * cc.r, s2);
+            }
+            if (atomic_dst) { atomicAdd(D.dz + o, dz); continue; }   // plain destination split over its fan-in
+            if (accumulate) dz += D.dz[o];
+            D.dz[o] = dz;
+          }
+        }
+        red[(0 * TC_WARPS + warp) * NT + col] = (double)s1;
+        red[(1 * TC_WARPS + warp) * NT + col] = (double)s2;
+      }
     }
   }
   if (has_norm && D.dstats) {
@@ -815,7 +893,17 @@ __global__ void __launch_bounds__(TC_NT, 1) fc_tc_wgrad_kernel(const __grid_cons
     }
   };
   constexpr int RPW = TC_BM / TC_WARPS;
-  if (!kn) {   // dW[n, j]: lanes run over j
+  const bool vec_out = !kn && !G.W2 && G.dW && (nvalid % 4 == 0) && (G.ldw % 4 == 0) && is_al16(G.dW);
+  if (vec_out) {   // dW[n, j], plain weight: one 16-byte reduction per 4 input features
+    for (int cbase = 0; cbase < nvalid; cbase += 128) {
+      const int col = cbase + 4 * lane;
+      if (col < nvalid)
+        for (int i = 0; i < RPW; ++i) {
+          const int row = warp * RPW + i;
+          if (row < mvalid) red_add_v4(G.dW + (int64_t)(m0 + row) * G.ldw + j0 + col, ld4s(ot + (size_t)row * ldo + col));
+        }
+    }
+  } else if (!kn) {   // dW[n, j]: lanes run over j
     for (int cbase = 0; cbase < nvalid; cbase += 32) {
       const int col = cbase + lane;
       if (col < nvalid)
