@@ -585,6 +585,111 @@ static int run_fwd(FcParams& p, cudaStream_t st) {
   return SWR_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// skinny layers (N <= 8 outputs: the MMoE / PLE gates, Linear(IN, n_expert), mmoe.py:28, ple.py:98-105)
+// A tiled GEMM wastes its tile on 4 output columns and pays a latency-bound k-loop per CTA; this forward kernel
+// reads each activation row once with 16-byte loads and keeps the whole (effective) weight in shared memory.
+// (A matching wgrad was tried and lost to the tiled kernel: 128 CTAs' atomics per weight element.)
+// ---------------------------------------------------------------------------------------
+constexpr int kSkinnyN = 8;
+constexpr int kSkinnyK = 1024;
+constexpr int kSkinnyRows = 32;     // forward: rows per CTA (4 per warp)
+
+__global__ void __launch_bounds__(256) fc_skinny_fwd_kernel(const __grid_constant__ FcParams p) {
+  extern __shared__ __align__(16) float sk[];
+  const FcGroup& G = p.g[blockIdx.y];
+  const int M = p.B, N = G.Y.n, K = G.A.n, Kp = (K + 3) & ~3;
+  float* Ws = sk;                    // [N][Kp] effective weight
+  float* kc = Ws + kSkinnyN * Kp;    // [3][Kp] mu, s, b of the input columns
+  __shared__ double sst[2 * kSkinnyN];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool plainA = (G.A.norm.mode == SWR_NORM_NONE && G.A.act == SWR_ACT_NONE);
+  const bool kn = (G.w_layout == SWR_W_KN);
+  for (int i = tid; i < N * Kp; i += 256) {
+    const int n = i / Kp, k = i - n * Kp;
+    float w = 0.f;
+    if (k < K) {
+      const int64_t o = kn ? ((int64_t)k * G.ldw + n) : ((int64_t)n * G.ldw + k);
+      w = __ldg(G.W + o);
+      if (G.W2) w *= __ldg(G.W2 + o);
+    }
+    Ws[i] = w;
+  }
+  if (!plainA)
+    for (int k = tid; k < Kp; k += 256) {
+      ColCoef c = {0.f, 0.f, 0.f, 0.f};
+      if (k < K) c = col_coef(G.A.norm, k, p.inv_count);
+      kc[k] = c.mu; kc[Kp + k] = c.s; kc[2 * Kp + k] = c.b;
+    }
+  if (tid < 2 * kSkinnyN) sst[tid] = 0.0;
+  __syncthreads();
+  const bool vecA = is_al16(G.A.raw) && (G.A.ld % 4 == 0);
+  const int actA = G.A.act;
+  float bias = 0.f;
+  if (lane < N) bias = ld_opt(G.bias, lane, 0.f) + ld_opt(G.bias2, lane, 0.f);
+  float s1 = 0.f, s2 = 0.f;          // lane n: moments of output column n over this warp's rows
+  float* Y = const_cast<float*>(G.Y.raw);
+  for (int j = 0; j < kSkinnyRows / 8; ++j) {
+    const int m = blockIdx.x * kSkinnyRows + warp * (kSkinnyRows / 8) + j;
+    if (m >= M) break;               // warp-uniform
+    float acc[kSkinnyN];
+#pragma unroll
+    for (int n = 0; n < kSkinnyN; ++n) acc[n] = 0.f;
+    for (int k4 = 4 * lane; k4 < Kp; k4 += 128) {
+      float4 x = load4_guard(G.A.raw, G.A.ld, m, k4, M, K, vecA);
+      if (!plainA) {
+        x.x = act_fwd(fmaf(x.x - kc[k4], kc[Kp + k4], kc[2 * Kp + k4]), actA);
+        x.y = act_fwd(fmaf(x.y - kc[k4 + 1], kc[Kp + k4 + 1], kc[2 * Kp + k4 + 1]), actA);
+        x.z = act_fwd(fmaf(x.z - kc[k4 + 2], kc[Kp + k4 + 2], kc[2 * Kp + k4 + 2]), actA);
+        x.w = act_fwd(fmaf(x.w - kc[k4 + 3], kc[Kp + k4 + 3], kc[2 * Kp + k4 + 3]), actA);
+      }
+#pragma unroll
+      for (int n = 0; n < kSkinnyN; ++n)
+        if (n < N) {   // padded k carry a zero weight
+          const float4 w = *reinterpret_cast<const float4*>(Ws + n * Kp + k4);
+          acc[n] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[n]))));
+        }
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int n = 0; n < kSkinnyN; ++n)
+      if (n < N) {
+        const float t = warp_sum(acc[n]);
+        if (lane == n) mine = t;
+      }
+    if (lane < N) {
+      float y = mine + bias;
+      if (G.e_act != SWR_ACT_NONE) y = act_fwd(y, G.e_act) * G.e_scale;
+      Y[(int64_t)m * G.Y.ld + lane] = y;
+      s1 += y; s2 = fmaf(y, y, s2);
+    }
+  }
+  if (G.stats_out) {
+    if (lane < N) { atomicAdd(&sst[2 * lane], (double)s1); atomicAdd(&sst[2 * lane + 1], (double)s2); }
+    __syncthreads();
+    if (tid < 2 * N) atomicAdd(G.stats_out + tid, sst[tid]);
+  }
+}
+
+static bool skinny_ok(const FcGroup* groups, int n_groups) {
+  for (int g = 0; g < n_groups; ++g)
+    if (groups[g].Y.n > kSkinnyN || groups[g].A.n > kSkinnyK) return false;
+  return n_groups > 0;
+}
+
+static int launch_fc_skinny_fwd(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st) {
+  FcParams p{};
+  int kmax = 0;
+  for (int g = 0; g < n_groups; ++g) { p.g[g] = groups[g]; kmax = max(kmax, groups[g].A.n); }
+  p.n_groups = n_groups; p.B = (int)B; p.inv_count = 1.0f / (float)B;
+  const size_t sm = sizeof(float) * (size_t)((kmax + 3) & ~3) * (kSkinnyN + 3);
+  int rc = set_smem(fc_skinny_fwd_kernel, sm);
+  if (rc) return rc;
+  fc_skinny_fwd_kernel<<<dim3(ceil_div(B, kSkinnyRows), n_groups), 256, sm, st>>>(p);
+  SWR_LAUNCH_OK("fc_skinny_fwd_kernel");
+  return SWR_OK;
+}
+
 // SWR_FC_AUTO: groups too narrow to fill a 128 x N accumulator tile (gates, towers' last layers) stay on the
 // FFMA kernels -- as CTAs of the tensor-core launch they would each hold a whole SM for a sliver of work.
 static bool tc_narrow(const FcGroup& g) { return g.Y.n < 32; }
@@ -611,7 +716,7 @@ int launch_fc_fwd(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t s
   if (rc) return rc;
   if (fc_tc_wanted(groups, n_groups, B))
     return split_by_width(groups, n_groups, [&](const FcGroup* g, int n) { return launch_fc_tc_fwd(g, n, B, st); },
-                          [&](const FcGroup* g, int n) { return launch_fc_fwd_simt(g, n, B, st); });
+                          [&](const FcGroup* g, int n) { return skinny_ok(g, n) ? launch_fc_skinny_fwd(g, n, B, st) : launch_fc_fwd_simt(g, n, B, st); });
   return launch_fc_fwd_simt(groups, n_groups, B, st);
 }
 
