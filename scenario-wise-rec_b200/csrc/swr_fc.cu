@@ -786,9 +786,9 @@ template <class C>
 static int run_wgrad(FcParams& p, cudaStream_t st) {
   int base = 0;
   for (int g = 0; g < p.n_groups; ++g) base += ceil_div(p.g[g].Y.n, C::BM) * ceil_div(p.g[g].A.n, C::BN);
-  // split the batch so the grid covers the machine about twice; keep >= 64 rows (4 k-steps) per split: the
+  // split the batch so the grid covers the machine about six times; keep >= 64 rows (4 k-steps) per split: the
   // narrow layers this kernel serves are latency-bound per k-step, so short chains on many CTAs win
-  int splits = max(1, min((2 * 148 + base - 1) / base, (p.B + 63) / 64));
+  int splits = max(1, min((6 * 148 + base - 1) / base, (p.B + 63) / 64));
   int rows = (p.B + splits - 1) / splits;
   rows = (rows + BK - 1) / BK * BK;
   splits = (p.B + rows - 1) / rows;
