@@ -386,6 +386,14 @@ def main():
         roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": (ach / pk["hbm"]) if ach else None, "traffic": None}
     roof.update(kernel=top["op"], kernel_ms=top["ms"], peak_source=pk["source"],
                 share_of_step=top["ms"] / max(sum(o["ms"] for o in ops), 1e-9), traffic=ncu_traffic(top["op"]))
+    # the top tensor-bound op as well (the dominant kernel may be the HBM-bound optimizer sweep)
+    ttop = next((o for o in ops if o["bound"] == "tensor" and o["work"]), None)
+    roof_t = None
+    if ttop is not None:
+        ach_t = ttop["work"] / (ttop["ms"] * 1e-3) / 1e12
+        roof_t = {"bound": "tensor", "kernel": ttop["op"], "kernel_ms": ttop["ms"], "achieved": ach_t, "peak": pk["bf16_sustained"],
+                  "unit": "TFLOP/s", "frac": ach_t / pk["bf16_sustained"], "traffic": ncu_traffic(ttop["op"]),
+                  "note": "algorithmic fp32 FLOPs; the 3xTF32 arithmetic issues 3x that on a pipe with half the bf16 rate"}
     sat = saturated_gather_scatter(feats, dev, pk) if rank == 0 else None
     gather = next((o for o in ops if o["op"] == "gather"), None)
     scatter = next((o for o in ops if o["op"] == "scatter"), None)
@@ -404,6 +412,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "roofline": roof,
+        "roofline_tensor": roof_t,
         "ops_ms": [{"op": o["op"], "ms": round(o["ms"], 5)} for o in ops[:14]],
         "ops_ms_total": round(sum(o["ms"] for o in ops), 5),
         "gather": None if not gather else {"ms": gather["ms"], "GBps": gather["work"] / gather["ms"] / 1e6, "frac_hbm": gather["work"] / gather["ms"] / 1e6 / pk["hbm"]},
