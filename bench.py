@@ -164,14 +164,14 @@ def run_reference(args, rank, world):
     n, dt = ref.time(args.steps, args.warmup)
     val = n * ref.B / dt
     sample = f"{n} full train steps of {args.workload} (B={ref.B}) after {args.warmup} warm-up"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": n, "warmup": args.warmup,
         "ms_per_step": dt / n * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": {"workload": args.workload, "device": "cpu", "path": "oracle/ref_models.py (torch CPU, same ATen ops as the reference)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": ref.cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    })
 
 
 # --------------------------------------------------------------------------------------------
@@ -270,7 +270,25 @@ def ncu_traffic(op_name):
 
 
 # --------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # Libraries write to stdout behind Python's back (NCCL prints its version banner there): keep file descriptor 1
+    # for the JSON line alone and send everything else to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -428,7 +446,7 @@ def main():
         line["cpu_baseline"] = {"value": n * ref.B / dt, "unit": UNIT, "cores": ref.cores, "kind": "port",
                                 "sample": f"{n} full train steps of {args.workload} (B={ref.B}) on the host, {dt:.1f} s"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # the captured step graphs hold NCCL work on the communicator: destroy_process_group() would wait on it
         # forever.  Everybody is past the last collective once the barrier returns; leave without the teardown.
