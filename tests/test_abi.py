@@ -55,3 +55,15 @@ def test_malformed_program_is_rejected_without_a_gpu():
     slots = np.zeros(1, dtype=np.uint64)
     st = N.lib().swr_program_run(recs.ctypes.data, 1, slots.ctypes.data, 1, None)
     assert st == -1 and "unknown op kind" in N.last_error()
+
+
+def test_fc_mode_switch_roundtrip():
+    """swr_set_fc_mode / swr_get_fc_mode need no device: the mode is process state read at launch time."""
+    prev = N.get_fc_mode()
+    assert prev in (N.FC_SIMT, N.FC_TC, N.FC_AUTO)
+    try:
+        assert N.set_fc_mode(N.FC_SIMT) == prev and N.get_fc_mode() == N.FC_SIMT
+        assert N.set_fc_mode(7) == N.FC_SIMT and N.get_fc_mode() == N.FC_SIMT      # out of range: ignored
+        assert N.set_fc_mode(N.FC_TC) == N.FC_SIMT and N.get_fc_mode() == N.FC_TC
+    finally:
+        N.set_fc_mode(prev)

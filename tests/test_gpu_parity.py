@@ -26,13 +26,26 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture
+def fc_mode(request):
+    """FC arithmetic for one test (swr_set_fc_mode): FC_SIMT = fp32 FFMA, FC_AUTO = default (tcgen05 on wide layers),
+    FC_TC = tcgen05 on every layer whose batch reaches 64 rows (odd widths, unaligned weights, partial k-blocks)."""
+    prev = N.set_fc_mode(request.param)
+    yield request.param
+    N.set_fc_mode(prev)
+
+
+FC_MODES = pytest.mark.parametrize("fc_mode", [N.FC_AUTO, N.FC_TC], ids=["auto", "tcgen05-everywhere"], indirect=True)
+
+
 def test_library_loads_on_device():
     assert N.lib().swr_abi_version() == N.ABI_VERSION
     assert N.lib().swr_device_check() == 0, N.last_error()
 
 
+@FC_MODES
 @pytest.mark.parametrize("name", golden_names())
-def test_golden(name):
+def test_golden(name, fc_mode):
     g = Golden(name)
     if not model_factory.supported(g.model):
         pytest.skip(f"{g.model} not lowered yet")
@@ -44,9 +57,10 @@ def test_golden(name):
     assert N.launch_count() > before, "no kernel of libswr_b200.so was launched"
 
 
+@FC_MODES
 @pytest.mark.parametrize("name", golden_names())
 @pytest.mark.parametrize("training", [True, False])
-def test_every_buffer_matches_interpreter(name, training):
+def test_every_buffer_matches_interpreter(name, training, fc_mode):
     """Runs the same records on both executors and compares every activation, statistic,
     gradient buffer and parameter gradient."""
     g = Golden(name)
@@ -111,13 +125,6 @@ def _oracle(model_name, cfg, x, y, state, dt):
     out = ref_models.forward(model_name, xx, st, cfg, training=True, bn_out=bn_out)
     ref_models.bce_loss(out, y.to(dt)).backward()
     return out.detach(), {k: v.grad for k, v in st.items() if v.requires_grad}, bn_out
-
-
-@pytest.fixture
-def fc_mode(request):
-    prev = N.set_fc_mode(request.param)
-    yield request.param
-    N.set_fc_mode(prev)
 
 
 @pytest.mark.parametrize("fc_mode", [N.FC_SIMT, N.FC_AUTO], ids=["ffma", "tcgen05"], indirect=True)
