@@ -61,6 +61,47 @@ def shard_of(full: torch.Tensor, info: ShardInfo) -> torch.Tensor:
     return out
 
 
+# ---- checkpoints in the reference's format (ctr_trainer.py:90-97, basic/callback.py:27) ----------
+def _sharded_params(model) -> Dict[str, "ShardInfo"]:
+    """state_dict key of every row-sharded table of ``model`` -> (ShardInfo, vocab_size)."""
+    from .basic.features import SparseFeature
+    out = {}
+    for feats in model._feature_lists():
+        for f in feats:
+            if isinstance(f, SparseFeature) and getattr(f, "shard", None) is not None:
+                for key, prm in model.named_parameters():
+                    if prm is f.get_embedding_layer().weight:
+                        out[key] = (f.shard, f.vocab_size)
+    return out
+
+
+def full_state_dict(model) -> Dict[str, torch.Tensor]:
+    """``model.state_dict()`` with every row-sharded table re-assembled to its full ``[vocab, E]`` shape under the
+    reference's key (collective: every rank of the shard group must call it; every rank gets the full dict, so a
+    ``.pth`` written by rank 0 loads into the reference model with ``strict=True``)."""
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    for key, (info, vocab) in _sharded_params(model).items():
+        local = sd[key].contiguous()
+        parts = [torch.empty_like(local) for _ in range(info.world)]
+        dist.all_gather(parts, local, group=info.group)
+        full = local.new_empty(vocab, local.shape[1])
+        for r, part in enumerate(parts):
+            n = (vocab - r + info.world - 1) // info.world      # rows r, r + R, r + 2R, ...
+            full[r::info.world] = part[:n]
+        sd[key] = full
+    return sd
+
+
+def load_full_state_dict(model, state: Dict[str, torch.Tensor], strict: bool = True):
+    """Load a reference-format state dict (full tables) into a model whose large tables are row-sharded: every rank
+    keeps rows ``rank, rank + R, ...`` of each sharded table (no communication)."""
+    state = dict(state)
+    for key, (info, vocab) in _sharded_params(model).items():
+        if key in state and state[key].shape[0] == vocab:
+            state[key] = shard_of(state[key], info)
+    return model.load_state_dict(state, strict=strict)
+
+
 # ---- local row gather / scatter through the C ABI (K1 / K2 on one field) ---------------------------------
 def local_gather(table: torch.Tensor, idx: torch.Tensor, out: torch.Tensor):
     """out[i] = table[idx[i]] (zero row when idx[i] is outside [0, rows)); no out-of-range flag."""

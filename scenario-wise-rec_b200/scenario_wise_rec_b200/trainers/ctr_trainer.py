@@ -168,7 +168,17 @@ class CTRTrainer(object):
                     break
         time_now = time.strftime("%m_%d_%H_%M", time.localtime(int(round(time.time() * 1000)) / 1000))
         name = self.model.__class__.__name__ + "_" + self.data_set_type + "_" + time_now + ".pth"
-        torch.save(self.model.state_dict(), os.path.join(self.model_path, name))
+        # same file as the reference writes (ctr_trainer.py:94-97).  With row-sharded tables the shards are gathered
+        # back into full [vocab, E] tables under the reference's keys first, and one rank writes the file.
+        from .. import parallel
+        if parallel._sharded_params(self.model):
+            import torch.distributed as dist
+            state = parallel.full_state_dict(self.model)
+            if dist.get_rank() != 0:
+                return
+        else:
+            state = self.model.state_dict()
+        torch.save(state, os.path.join(self.model_path, name))
 
     # ---- evaluation ------------------------------------------------------------------------------
     def _predict_batches(self, model, data_loader, desc):

@@ -156,3 +156,42 @@ def _sharded_equals_replicated(rank, world):
 
 def test_sharded_table_equals_replicated():
     _spawn(_sharded_equals_replicated)
+
+
+# ---- checkpoints of row-sharded models keep the reference's format ---------------------
+def _sharded_checkpoint_roundtrip(rank, world):
+    from golden_util import Golden
+    import model_factory
+    from scenario_wise_rec_b200 import parallel
+    import scenario_wise_rec_b200.models.multi_domain as M
+    g = Golden("mmoe_small")
+    cfg = g.cfg
+
+    def build(shard):
+        feats = model_factory.features(cfg["features"])
+        names = parallel.shard_features(feats, min_rows=40) if shard else []
+        m = M.MMOE(feats, cfg["domain_num"], n_expert=cfg["n_expert"], expert_params={"dims": list(cfg["expert_dims"])},
+                   tower_params={"dims": list(cfg["tower_dims"])})
+        return m, names
+
+    sh, names = build(True)
+    assert names
+    # reference-format state (full tables) -> sharded model: every rank keeps its rows
+    parallel.load_full_state_dict(sh, g.state0)
+    for n in names:
+        k = f"embedding.embed_dict.{n}.weight"
+        full = g.state0[k]
+        mine = full[rank::world]
+        assert torch.equal(sh.state_dict()[k][:mine.shape[0]], mine)
+    # sharded model -> reference-format state: identical to what was loaded, on every rank, and loadable
+    # (strict) into an unsharded model
+    sd = parallel.full_state_dict(sh)
+    assert set(sd) == set(g.state0)
+    for k, v in g.state0.items():
+        assert sd[k].shape == v.shape and torch.equal(sd[k], v), k
+    rep, _ = build(False)
+    rep.load_state_dict(sd, strict=True)
+
+
+def test_sharded_checkpoint_roundtrip():
+    _spawn(_sharded_checkpoint_roundtrip)
