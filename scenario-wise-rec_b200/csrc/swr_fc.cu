@@ -703,7 +703,11 @@ static int split_by_width(const FcGroup* groups, int n_groups, F1 run_tc, F2 run
     else wide[nw++] = groups[g];
   }
   if (nn) { int rc = run_simt(narrow, nn); if (rc) return rc; }
-  if (nw) { int rc = run_tc(wide, nw); if (rc) return rc; }
+  if (nw) {
+    int rc = run_tc(wide, nw);
+    if (rc == SWR_ERR_UNSUPPORTED) rc = run_simt(wide, nw);   // a shape the tensor-core tiles cannot hold: FFMA serves everything
+    if (rc) return rc;
+  }
   return SWR_OK;
 }
 
@@ -777,7 +781,10 @@ int launch_fc_dgrad(const FcGroup* groups, const int* dst_of, int n_groups, int6
   p.dst_group[n_dst] = n_groups;
   p.n_dst = n_dst;
   p.n_groups = n_groups; p.B = (int)B; p.inv_count = 1.0f / (float)B;
-  if (fc_tc_wanted(groups, n_groups, B)) return launch_fc_tc_dgrad(groups, p.dst_group, n_dst, n_groups, B, st);
+  if (fc_tc_wanted(groups, n_groups, B)) {
+    rc = launch_fc_tc_dgrad(groups, p.dst_group, n_dst, n_groups, B, st);
+    if (rc != SWR_ERR_UNSUPPORTED) return rc;   // else: a shape the tensor-core tiles cannot hold, FFMA serves it
+  }
   if (kd_max > 16) return tiles128 >= 296 ? run_dgrad<CfgWide>(p, st) : run_dgrad<CfgMid>(p, st);
   return run_dgrad<CfgNarrowS>(p, st);
 }

@@ -1074,7 +1074,8 @@ int launch_fc_tc_dgrad(const FcGroup* groups, const int* dst_group_in, int n_dst
   // A single plain destination (the embedding output: no norm, no activation, so its epilogue is a bare store) with a
   // long fan-in is split into a few partial fan-ins that add atomically: each CTA then stages a wider column tile
   // for a shorter contraction, and the operand rows restaged per column tile drop by about a third.
-  if (n_dst == 1 && n_groups >= 2 && kb >= 16) {
+  static const bool split_fanin = !(getenv("SWR_TC_DGRAD_SPLIT") && atoi(getenv("SWR_TC_DGRAD_SPLIT")) == 0);
+  if (split_fanin && n_dst == 1 && n_groups >= 2 && kb >= 16) {
     const ActDev& D = groups[0].A;
     const bool plain = D.norm.mode == SWR_NORM_NONE && D.act == SWR_ACT_NONE;
     const int ntiles_min = ceil_div(D.n, 256);
