@@ -381,7 +381,8 @@ SWR_API int swr_program_run(const swr_rec_t* recs, int32_t n_recs, void* const* 
       case SWR_OP_BMV_BWD: rc = run_bmv(h, subs, true, c, st); break;
       case SWR_OP_BCE:
         rc = launch_bce(static_cast<const float*>(c.slot(h.s[0])), c.slot(h.s[1]), h.i[1], static_cast<float*>(c.slot(h.s[2])),
-                        static_cast<float*>(c.slot(h.s[3])), static_cast<const int32_t*>(c.slot(h.s[4])), h.i[2], h.i[0], st);
+                        static_cast<float*>(c.slot(h.s[3])), static_cast<const int32_t*>(c.slot(h.s[4])), h.i[2], h.i[0],
+                        h.f[0] != 0.f ? h.f[0] : 1.f, st);
         break;
       case SWR_OP_ADAM:
         rc = launch_adam(static_cast<float*>(c.slot(h.s[0])), static_cast<float*>(c.slot(h.s[1])), static_cast<float*>(c.slot(h.s[2])),

@@ -147,7 +147,7 @@ int launch_bmv_bwd(const BmvLaunch& m, cudaStream_t st);
 
 // ---- trainer-side ops (swr_train.cu) ---------------------------------------------------------------
 int launch_bce(const float* pred, const void* label, int label_dtype, float* gout, float* loss_ring, const int32_t* ctrl,
-               int ring, int64_t B, cudaStream_t st);
+               int ring, int64_t B, float gscale, cudaStream_t st);
 int launch_adam(float* p, float* g, float* m, float* v, const float* hyper, int64_t n, int zero_grad, cudaStream_t st);
 
 }  // namespace swr

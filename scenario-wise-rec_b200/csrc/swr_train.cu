@@ -15,10 +15,10 @@ namespace swr {
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) bce_kernel(const float* __restrict__ pred, const void* __restrict__ label, int label_dtype,
                                                    float* __restrict__ gout, float* __restrict__ loss_ring,
-                                                   const int32_t* __restrict__ ctrl, int ring, int B) {
+                                                   const int32_t* __restrict__ ctrl, int ring, int B, float gscale) {
   __shared__ double red[32];
   double acc = 0.0;
-  const float inv = 1.0f / (float)B;
+  const float inv = gscale / (float)B;   // gscale = 1 / world when data-parallel gradients are summed instead of averaged
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     const float p = pred[b], y = load_scalar(label, label_dtype, b);
     const float lp = fmaxf(logf(p), -100.f), l1p = fmaxf(logf(1.f - p), -100.f);
@@ -39,10 +39,10 @@ __global__ void __launch_bounds__(1024) bce_kernel(const float* __restrict__ pre
 }
 
 int launch_bce(const float* pred, const void* label, int label_dtype, float* gout, float* loss_ring, const int32_t* ctrl,
-               int ring, int64_t B, cudaStream_t st) {
+               int ring, int64_t B, float gscale, cudaStream_t st) {
   if (B <= 0) return SWR_OK;
   if (!pred || !label) { set_error("bce: null operand"); return SWR_ERR_INVALID; }
-  bce_kernel<<<1, 1024, 0, st>>>(pred, label, label_dtype, gout, loss_ring, ctrl, ring > 0 ? ring : 1, (int)B);
+  bce_kernel<<<1, 1024, 0, st>>>(pred, label, label_dtype, gout, loss_ring, ctrl, ring > 0 ? ring : 1, (int)B, gscale);
   SWR_LAUNCH_OK("bce_kernel");
   return SWR_OK;
 }

@@ -21,6 +21,8 @@ from __future__ import annotations
 import math
 from typing import Dict, List, Optional
 
+import os
+
 import numpy as np
 import torch
 
@@ -241,7 +243,7 @@ class FusedTrainStep:
         self.ptrs = ptrs
 
         # ---- record lists
-        def rec(kind, ints=(), slots=()):
+        def rec(kind, ints=(), slots=(), floats=()):
             r = np.zeros((), dtype=N.REC_DTYPE)
             r["kind"] = kind
             r["s"][:] = -1
@@ -249,10 +251,16 @@ class FusedTrainStep:
                 r["i"][i] = v
             for i, v in enumerate(slots):
                 r["s"][i] = v
+            for i, v in enumerate(floats):
+                r["f"][i] = v
             return r
 
         split = ProgramBuilder._split64
-        bce = rec(N.OP_BCE, [self.B, N.DT_F32, RING], [prog.out_slot, X["label"], prog.gout_slot, X["loss"], X["ctrl"]])
+        # Data-parallel table gradients as rows instead of a dense all-reduce (see _setup_sparse_sync): every rank then
+        # scales its loss gradient by 1 / world, so that cross-rank *sums* are the global-batch mean.
+        self.sparse_sync = self._setup_sparse_sync(prog, ptrs)
+        gscale = 1.0 / self.sparse_sync["world"] if self.sparse_sync else 1.0
+        bce = rec(N.OP_BCE, [self.B, N.DT_F32, RING], [prog.out_slot, X["label"], prog.gout_slot, X["loss"], X["ctrl"]], [gscale])
         zeros = [rec(N.OP_ZERO, split(4 * gsize[a]), [self.arena_slots[a][1]]) for a in flat.size]
         adams = [rec(N.OP_ADAM, [*split(flat.size[a]), 0], [*self.arena_slots[a], X["hyper"]]) for a in flat.opt_arenas
                  if flat.size[a] > 4 or a == "dense"]
@@ -277,6 +285,70 @@ class FusedTrainStep:
         self.use_graph = use_graph
         self._warm = 0
 
+    # ---- data-parallel table gradients as rows -------------------------------------------------------------------
+    def _setup_sparse_sync(self, prog, ptrs):
+        """Replicated tables under data parallelism: the dense gradient of a table is non-zero on at most B rows, so
+        instead of all-reducing the whole table-gradient arena (100 MB per step at cfg2) every rank all-gathers the
+        gradient of the embedding-layer output [B, IN] and the staged index columns (7 MB) and replays the K2 scatter
+        of the backward program on each peer's block.  Same sums as the dense all-reduce, in a different order.
+        Returns None when it does not apply (single process, row-sharded fields, tiny tables, or SWR_DP_SPARSE=0)."""
+        import torch.distributed as dist
+        if self.grad_sync is None or prog.virtual_fields or not (dist.is_available() and dist.is_initialized()):
+            return None
+        mode = os.environ.get("SWR_DP_SPARSE", "auto")
+        if mode == "0":
+            return None
+        world, rank = dist.get_world_size(), dist.get_rank()
+        recs = prog.recs_bwd
+        blocks = []          # (header index, number of sub-records)
+        i = 0
+        while i < len(recs):
+            ns = int(recs[i]["n_sub"])
+            if int(recs[i]["kind"]) == N.OP_SCATTER:
+                blocks.append((i, ns))
+            i += 1 + ns
+        if world < 2 or not blocks or "emb" not in self.flat.g:
+            return None
+        emb_bytes = 4 * self.flat.g["emb"].numel()
+        dz_views, scat = [], []
+        for hi, ns in blocks:
+            d = prog.slot_desc[int(recs[hi]["s"][0])]
+            if d[0] != "ws32":
+                return None
+            dz_views.append((int(recs[hi]["s"][0]), self.runner.ws32[d[1]:d[1] + d[2]]))
+            scat.append(recs[hi:hi + 1 + ns])
+        gathered_bytes = world * (sum(4 * v.numel() for _, v in dz_views) + self.stage_bytes)
+        if mode != "1" and emb_bytes < 2 * gathered_bytes:
+            return None       # small tables: the dense all-reduce moves less
+        dev = self.device
+        g_stage = torch.zeros(world, self.stage_bytes, dtype=torch.uint8, device=dev)
+        g_dz = [torch.zeros(world, v.numel(), dtype=torch.float32, device=dev) for _, v in dz_views]
+        input_slots = {slot: name for name, slot in prog.inputs.items() if name in self.layout}
+        peer_ptrs = []
+        for r in range(world):
+            if r == rank:
+                continue
+            pr = ptrs.copy()
+            for (slot, _v), buf in zip(dz_views, g_dz):
+                pr[slot] = buf[r].data_ptr()
+            for slot, name in input_slots.items():
+                pr[slot] = g_stage[r].data_ptr() + self.layout[name][0]
+            peer_ptrs.append(pr)
+        return {"world": world, "rank": rank, "recs": np.concatenate(scat).astype(N.REC_DTYPE), "dz": dz_views, "g_dz": g_dz,
+                "g_stage": g_stage, "peer_ptrs": peer_ptrs}
+
+    def _sparse_grad_sync(self, stream):
+        import torch.distributed as dist
+        ss = self.sparse_sync
+        dist.all_gather_into_tensor(ss["g_stage"].view(-1), self.dev_stage)
+        for (_slot, v), buf in zip(ss["dz"], ss["g_dz"]):
+            dist.all_gather_into_tensor(buf.view(-1), v)
+        for pr in ss["peer_ptrs"]:                       # K2 scatter of each peer's rows into the local table gradients
+            N.program_run(ss["recs"], pr, stream)
+        for name, a in self.flat.g.items():              # everything else (tower / expert / gate weights): summed densely
+            if name == "dense" and a.numel() > 1:
+                dist.all_reduce(a, op=dist.ReduceOp.SUM)
+
     # ---- device work of one step (graph-capturable: no syncs, no allocations) ------------------------
     def _body(self):
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -287,7 +359,9 @@ class FusedTrainStep:
             for f, _idx, gv, gs in self._vf:           # backward half: route virtual-table gradients to their owners
                 if gv is not None and gs is not None:
                     self.exchange.route_grad(f, gv, gs)
-            if self.grad_sync is not None:
+            if self.sparse_sync is not None:
+                self._sparse_grad_sync(stream)
+            elif self.grad_sync is not None:
                 self.grad_sync(self.flat.g)
             N.program_run(self.recs_b, self.ptrs, stream)
         N.memcpy_async(self.loss_ring_host.data_ptr(), self.loss_ring_dev.data_ptr(), 4 * RING, stream)

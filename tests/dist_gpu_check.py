@@ -25,22 +25,27 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     opt = {"lr": 1e-2, "weight_decay": 1e-4}
 
-    # 1. data parallel (fused step, all-reduce inside the graph) == one process on the global batch (no batch coupling)
+    # 1. data parallel (fused step, gradient exchange inside the graph) == one process on the global batch (no batch
+    #    coupling), with the table gradients all-reduced densely and exchanged as rows (SWR_DP_SPARSE)
     g = Golden("m3oe_small")
     half = g.B // world
     sl = slice(rank * half, (rank + 1) * half)
-    m = model_factory.build(g.model, g.cfg); m.load_state_dict(g.state0)
-    t = CTRTrainer(m, "dp", optimizer_params=opt, device=str(dev)); t.enable_data_parallel(); m.train()
-    ref = model_factory.build(g.model, g.cfg); ref.load_state_dict(g.state0)
-    tr = CTRTrainer(ref, "single", optimizer_params=opt, device=str(dev)); ref.train()
-    for _ in range(5):
-        t.train_step({k: v[sl] for k, v in g.x.items()}, g.y[sl])
-        tr.train_step(g.x, g.y)
-    torch.cuda.synchronize()
-    fs = next(iter(t._steps.values()))
-    assert fs.graph is not None, "DP step was not captured in a CUDA graph"
-    for k, v in ref.state_dict().items():
-        torch.testing.assert_close(m.state_dict()[k], v, atol=5e-6, rtol=2e-4, msg=lambda s, k=k: f"dp {k}: {s}")
+    for sparse in ("0", "1"):
+        os.environ["SWR_DP_SPARSE"] = sparse
+        m = model_factory.build(g.model, g.cfg); m.load_state_dict(g.state0)
+        t = CTRTrainer(m, "dp", optimizer_params=opt, device=str(dev)); t.enable_data_parallel(); m.train()
+        ref = model_factory.build(g.model, g.cfg); ref.load_state_dict(g.state0)
+        tr = CTRTrainer(ref, "single", optimizer_params=opt, device=str(dev)); ref.train()
+        for _ in range(5):
+            t.train_step({k: v[sl] for k, v in g.x.items()}, g.y[sl])
+            tr.train_step(g.x, g.y)
+        torch.cuda.synchronize()
+        fs = next(iter(t._steps.values()))
+        assert fs.graph is not None, "DP step was not captured in a CUDA graph"
+        assert (fs.sparse_sync is not None) == (sparse == "1"), (sparse, fs.sparse_sync is not None)
+        for k, v in ref.state_dict().items():
+            torch.testing.assert_close(m.state_dict()[k], v, atol=5e-6, rtol=2e-4, msg=lambda s, k=k: f"dp sparse={sparse} {k}: {s}")
+    os.environ.pop("SWR_DP_SPARSE", None)
 
     # 2. row-sharded tables == replicated tables, fused and generic paths
     g = Golden("mmoe_small")
