@@ -10,14 +10,18 @@
 // three MMAs  lo*hi + hi*lo + hi*hi  into the same accumulator ("3xTF32", error ~2^-21 relative).
 //
 // Operands cannot come through TMA because they are *computed* on the way in (DESIGN.md "Lazy
-// activations"): the CTA's 256 threads load raw values with 16-byte read-only loads (register-prefetched
+// activations"): the CTA's 512 threads load raw values with 16-byte read-only loads (register-prefetched
 // one k-block ahead), apply the lazy BatchNorm/activation (forward), the BatchNorm-backward affine map
-// (dgrad/wgrad) or the STAR weight product, split, and store straight into the 128-byte swizzled tile
-// layout the MMA unit reads (swr_tc.cuh).  One elected thread issues the MMAs; tcgen05.commit arrives on
-// an mbarrier per pipeline stage to hand the stage back to the stagers.  The epilogue pulls the tile out
-// of TMEM with tcgen05.ld (one row per thread), transposes it through shared memory, and runs the same
-// fused tails as the SIMT kernels (bias / GateNU activation / fp64 column moments; act' + BatchNorm stage-1
-// sums; weight-gradient atomics) with coalesced global accesses.
+// (dgrad/wgrad) or the STAR weight product, and split.  Where the results go:
+//   forward, dgrad (TS mode)  the 128-row operand (activations / dY) goes registers -> TMEM with tcgen05.st
+//                             and is the MMA's A operand in tensor memory; the weight tile goes to shared
+//                             memory in the 128-byte swizzled layout the MMA unit reads (swr_tc.cuh)
+//   wgrad (SS mode)           both operands (dY^T and the activations, batch-strided) go to shared memory
+// Lane 0 of warp (k-block mod 16) issues that block's MMAs once every thread has arrived on the stage's
+// mbarrier; tcgen05.commit arrives on a second mbarrier to hand the stage back to the stagers.  The epilogue
+// pulls the tile out of TMEM with tcgen05.ld (one row per thread), transposes it through shared memory, and
+// runs the same fused tails as the SIMT kernels (bias / GateNU activation / fp64 column moments; act' +
+// BatchNorm stage-1 sums; weight-gradient reductions) with 16-byte coalesced global accesses.
 #include "swr_common.cuh"
 #include "swr_launch.h"
 #include "swr_tc.cuh"
