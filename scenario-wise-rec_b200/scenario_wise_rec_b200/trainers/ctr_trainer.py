@@ -190,28 +190,42 @@ class CTRTrainer(object):
         if hasattr(model, "check_indices"):
             model.check_indices()
 
+    # The reference calls ``.tolist()`` on the labels and the predictions of every batch (ctr_trainer.py:109-110,
+    # 130-131, 164): one host sync per batch.  Here the predictions stay on the device until the loader is exhausted
+    # and come back in ONE copy; the metric functions then receive the same Python lists as in the reference.
+    @staticmethod
+    def _to_list(chunks):
+        if not chunks:
+            return []
+        return torch.cat([c.reshape(-1) for c in chunks]).cpu().tolist()
+
     def evaluate(self, model, data_loader, mode="val"):
         from sklearn.metrics import log_loss
         targets, predicts = [], []
         for _x, y, y_pred in self._predict_batches(model, data_loader, "validation"):
-            targets.extend(y.tolist())
-            predicts.extend(y_pred.tolist())
+            targets.append(y)
+            predicts.append(y_pred)
+        targets, predicts = self._to_list(targets), self._to_list(predicts)
         return self.evaluate_fn(targets, predicts), log_loss(targets, predicts)
 
     def evaluate_multi_domain_loss(self, model, data_loader, domain_num):
         from sklearn.metrics import log_loss
-        t_all, p_all = [], []
-        t_dom = [[] for _ in range(domain_num)]
-        p_dom = [[] for _ in range(domain_num)]
+        t_chunks, p_chunks, d_chunks = [], [], []
         for x_dict, y, y_pred in self._predict_batches(model, data_loader, "validation"):
-            dom = x_dict["domain_indicator"].cpu()
-            y, y_pred = y.cpu(), y_pred.cpu()
-            t_all.extend(y.tolist())
-            p_all.extend(y_pred.tolist())
-            for d in range(domain_num):
-                m = dom == d
-                t_dom[d].extend(y[m].tolist())
-                p_dom[d].extend(y_pred[m].tolist())
+            t_chunks.append(y)
+            p_chunks.append(y_pred)
+            d_chunks.append(x_dict["domain_indicator"])
+        if not p_chunks:
+            return [None] * domain_num, [None] * domain_num, None, None
+        y = torch.cat([c.reshape(-1) for c in t_chunks]).cpu()
+        y_pred = torch.cat([c.reshape(-1) for c in p_chunks]).cpu()
+        dom = torch.cat([c.reshape(-1) for c in d_chunks]).cpu()
+        t_all, p_all = y.tolist(), y_pred.tolist()
+        t_dom, p_dom = [], []
+        for d in range(domain_num):
+            m = dom == d
+            t_dom.append(y[m].tolist())
+            p_dom.append(y_pred[m].tolist())
         logloss_d = [log_loss(t_dom[d], p_dom[d]) if t_dom[d] else None for d in range(domain_num)]
         auc_d = [self.evaluate_fn(t_dom[d], p_dom[d]) if t_dom[d] else None for d in range(domain_num)]
         total_logloss = log_loss(t_all, p_all) if p_all else None
@@ -221,5 +235,5 @@ class CTRTrainer(object):
     def predict(self, model, data_loader):
         predicts = []
         for _x, _y, y_pred in self._predict_batches(model, data_loader, "predict"):
-            predicts.extend(y_pred.tolist())
-        return predicts
+            predicts.append(y_pred)
+        return self._to_list(predicts)
