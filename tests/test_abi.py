@@ -67,3 +67,20 @@ def test_fc_mode_switch_roundtrip():
         assert N.set_fc_mode(N.FC_TC) == N.FC_SIMT and N.get_fc_mode() == N.FC_TC
     finally:
         N.set_fc_mode(prev)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/swr_b200.h compiles as C99 with nothing but <stdint.h>, and a C program
+    links against libswr_b200.so and calls it (no device needed for swr_abi_version)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "swr_b200.h"\nint main(void) { return swr_abi_version() == SWR_ABI_VERSION ? 0 : 1; }\n')
+    libdir = os.path.dirname(N.LIB_PATH) if hasattr(N, "LIB_PATH") else os.path.join(ROOT, "scenario-wise-rec_b200", "scenario_wise_rec_b200")
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-l:libswr_b200.so", f"-Wl,-rpath,{libdir}"], check=True, capture_output=True)
+    assert subprocess.run([str(exe)]).returncode == 0
