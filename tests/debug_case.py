@@ -1,5 +1,5 @@
 """Development aid: run one BASELINE-shaped case on the CUDA path and on the CPU interpreter (same records),
-report every workspace buffer / parameter gradient that differs.  usage: python tools/debug_case.py <case> [B]"""
+report every workspace buffer / parameter gradient that differs.  usage: python tests/debug_case.py <case> [B]"""
 import copy, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "scenario-wise-rec_b200"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):

@@ -1,5 +1,5 @@
 """Development aid: parameter-gradient errors of one BASELINE case under each FC arithmetic mode, vs the float64 oracle.
-usage: python tools/tc_debug.py <case> [repeats]"""
+usage: python tests/tc_debug.py <case> [repeats]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "scenario-wise-rec_b200"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):

@@ -143,7 +143,7 @@ def test_baseline_shapes_vs_oracle(case, fc_mode):
     same-signed per-sample terms which nearly cancel over the batch (30 % positive labels here) keeps the bias
     while the sum shrinks: up to ~5e-3 of max|g| on such components (the fp32 CPU reference itself is 1e-3 from
     float64 there).  Its per-element error (~1e-6 relative, ten times fp32's) also moves a few more pre-activations
-    across 0 than the fp32 paths do (measured on cfg2: rows 495, 717, 1613 of 4096, tools/debug_case.py); each
+    across 0 than the fp32 paths do (measured on cfg2: rows 495, 717, 1613 of 4096, tests/debug_case.py); each
     flipped row changes a weight gradient by that sample's own contribution, ~1/sqrt(B) of max|g|, spread over
     the whole tensor.  The tensor-core bound is therefore max-err <= max(1e-2, 8 x fp32 noise, 2/sqrt(B)) and
     relative L2 <= max(1e-2, 4 x fp32 noise, 2/sqrt(B)); a tiling / indexing bug is O(1) in both, and the small golden cases, the
