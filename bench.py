@@ -40,6 +40,7 @@ import workloads  # noqa: E402
 
 METRIC = "CTR training samples/sec (bs=4096 per GPU)"
 UNIT = "samples/s"
+NB_ROTATE = 8        # distinct batches, rotated (different rows touched every step)
 
 
 def peaks():
@@ -55,50 +56,70 @@ def peaks():
 # clocks
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons polled in-process through NVML every ~2 ms on a thread, from the start of the
+    warm-up to the end of the timed regions (a 14 ms timed region is invisible to ``nvidia-smi -lms 100``).
+    ``mark()`` brackets the timed regions; ``summary()`` reports the samples inside them (and the total)."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.marks = index, [], []
+        self._stop = threading.Event()
+        self.t = None
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical(index))
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    @staticmethod
+    def _physical(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                return int(ids[index])
+        return index
 
     def __enter__(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+        if self.h is not None:
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
-        except OSError:
-            self.proc = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _poll(self):
+        nv = self.nv
+        bits = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((time.perf_counter(), sm, tuple(n for n, b in bits if r & b)))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def mark(self):
+        self.marks.append(time.perf_counter())
 
     def __exit__(self, *a):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=3)
-            except subprocess.TimeoutExpired:
-                self.proc.kill()
+        self._stop.set()
+        if self.t is not None:
             self.t.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            if len(r) < 6:
-                continue
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        spans = list(zip(self.marks[0::2], self.marks[1::2]))
+        inside = [r for r in self.rows if any(a <= r[0] <= b for a, b in spans)] if spans else []
+        use = inside if inside else self.rows
+        if not use:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        reasons = sorted({n for r in use for n in r[2]})
+        return {"sm_mhz": float(np.median([r[1] for r in use])), "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "samples": len(use), "samples_in_timed_region": len(inside), "samples_total": len(self.rows),
+                "how": "NVML polled every ~2 ms from warm-up to the end of the timed regions"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -156,19 +177,54 @@ class CpuReference:
         return n, dt
 
 
+def base_config(args, world, parallelism=None):
+    """``config`` of the JSON line: identical keys (and, for the same flags, values) in both arms."""
+    model_name, cfg, B = workloads.CASES[args.workload]
+    feats = workloads.all_feature_specs(cfg)
+    if parallelism is None:
+        parallelism = "single" if world == 1 else (f"dp{world}" if args.shard_min_rows <= 0 else f"dp{world}+rowshard")
+    return {"workload": args.workload, "model": model_name, "batch_per_gpu": B, "global_batch": B * world, "parallelism": parallelism,
+            "shard_min_rows": args.shard_min_rows if world > 1 else 0,
+            "l2": "working set per step (tables + dense grads + Adam moments, %.0f MB) exceeds the 126 MB L2; %d rotating batches"
+                  % (4 * workloads.table_bytes(feats) / 1e6, NB_ROTATE),
+            "optimizer": "Adam(lr=1e-3, weight_decay=1e-5)"}
+
+
+def reference_arm(args, device, steps, warmup, budget_s=None):
+    """The unmodified reference (baseline/_ref, tools/ref_arm.py) through its own CTRTrainer.train_one_epoch on
+    ``device``; falls back to the oracle port on the CPU when baseline/_ref did not travel.  -> dict for the line."""
+    import ref_arm
+    model_name, cfg, B = workloads.CASES[args.workload]
+    feats = workloads.all_feature_specs(cfg)
+    batches = [workloads.make_batch(feats, B, cfg["domain_num"], seed=100 + i, pin=(device != "cpu")) for i in range(4)]
+    if ref_arm.available():
+        arm = ref_arm.ReferenceArm(model_name, cfg, device=device)
+        n, dt = arm.time(batches, steps, warmup, budget_s=budget_s)
+        kind, cores = "reference", arm.cores
+        path = "baseline/_ref scenario_wise_rec (unmodified): models.multi_domain.%s + trainers.CTRTrainer.train_one_epoch" % model_name
+    else:
+        if device != "cpu":
+            return None
+        ref = CpuReference(args.workload)
+        n, dt = ref.time(steps, warmup, budget_s=budget_s)
+        kind, cores, path = "port", ref.cores, "oracle/ref_models.py (baseline/_ref missing)"
+    return {"value": n * B / dt, "unit": UNIT, "cores": cores, "kind": kind, "steps": n, "ms_per_step": dt / n * 1e3, "device": device,
+            "path": path, "sample": f"{n} full train steps of {args.workload} (B={B}) after {warmup} warm-up, {dt:.1f} s"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    ref = CpuReference(args.workload)
-    n, dt = ref.time(args.steps, args.warmup)
-    val = n * ref.B / dt
-    sample = f"{n} full train steps of {args.workload} (B={ref.B}) after {args.warmup} warm-up"
+    # bounded: the whole run must end within a few minutes whatever --steps says
+    r = reference_arm(args, "cpu", args.steps, min(args.warmup, 3), budget_s=args.ref_budget)
+    val = r["value"]
     emit({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": n, "warmup": args.warmup,
-        "ms_per_step": dt / n * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": args.workload, "device": "cpu", "path": "oracle/ref_models.py (torch CPU, same ATen ops as the reference)"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": ref.cores, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"], "warmup": min(args.warmup, 3),
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": base_config(args, world),
+        "reference_path": r["path"],
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
@@ -297,6 +353,10 @@ def main():
     ap.add_argument("--workload", default=workloads.DEFAULT_CASE, choices=sorted(workloads.CASES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--ref-budget", type=float, default=60.0, help="seconds of CPU work for --impl reference")
+    ap.add_argument("--eager-budget", type=float, default=6.0, help="seconds for the eager-CUDA run of the unmodified reference")
+    ap.add_argument("--shard-min-rows", type=int, default=30000,
+                    help="with more than one GPU, row-shard every table with at least this many rows (0: replicate all tables)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -330,7 +390,7 @@ def main():
         trainer.enable_data_parallel()
     model.train()
 
-    NB = 8                                   # distinct batches, rotated (different rows touched every step)
+    NB = NB_ROTATE
     host = [workloads.make_batch(feats, B, cfg["domain_num"], seed=1000 * rank + i, pin=True) for i in range(NB)]
     fs = trainer.packer(host[0][0])          # the fused step (one CUDA graph) for this batch shape
     devb = [fs.pack(x, y, device=dev) for x, y in host]      # device-resident batches in the staging layout
@@ -365,11 +425,13 @@ def main():
     def run_e2e(steps):                      # the public API on pinned host batches (H2D + loss D2H inside)
         trainer.train_one_epoch([host[i % NB] for i in range(steps)])
 
-    run_resident(args.warmup)
-    run_e2e(max(args.warmup, 3))
     with ClockSampler(local) as clk:
+        run_resident(args.warmup)
+        run_e2e(max(args.warmup, 3))
+        clk.mark()
         ms, wall, _ = timed(run_resident, args.steps)
         ms_e2e, wall_e2e, _ = timed(run_e2e, args.steps)
+        clk.mark()
     model.check_indices()
     value = world * B * args.steps / (ms * 1e-3)
     e2e = world * B * args.steps / (max(ms_e2e, wall_e2e) * 1e-3)
@@ -420,11 +482,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": args.workload, "model": model_name, "batch_per_gpu": B, "global_batch": B * world,
-                   "parallelism": f"dp{world}" if world > 1 else "single",
-                   "l2": "working set per step (tables + dense grads + Adam moments, %.0f MB) exceeds the 126 MB L2; %d rotating batches"
-                         % (4 * workloads.table_bytes(feats) / 1e6, NB),
-                   "optimizer": "Adam(lr=1e-3, weight_decay=1e-5)"},
+        "config": base_config(args, world),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 256, "ms_per_step": max(ms_e2e, wall_e2e) / args.steps,
                 "api": "CTRTrainer.train_one_epoch(list of pinned host (x_dict, y) batches)"},
         "gpu_launches": int(launches),
@@ -440,11 +498,14 @@ def main():
         "wall_ms_per_step": wall / args.steps,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # the reference itself (unmodified, baseline/_ref) on this box: eager PyTorch on cuda:0 -- the bar SURVEY.md 8d
+        # sets -- and on the host cores; both through its own CTRTrainer.train_one_epoch with host batches
+        eager = reference_arm(args, str(dev), 200, 3, budget_s=args.eager_budget)
+        if eager is not None:
+            line["eager_cuda_baseline"] = {k: eager[k] for k in ("value", "unit", "kind", "ms_per_step", "device", "path", "sample")}
         torch.set_num_threads(os.cpu_count() or 1)
-        ref = CpuReference(args.workload)
-        n, dt = ref.time(10_000, 2, budget_s=args.cpu_budget)
-        line["cpu_baseline"] = {"value": n * ref.B / dt, "unit": UNIT, "cores": ref.cores, "kind": "port",
-                                "sample": f"{n} full train steps of {args.workload} (B={ref.B}) on the host, {dt:.1f} s"}
+        cpu = reference_arm(args, "cpu", 10_000, 2, budget_s=args.cpu_budget)
+        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if rank == 0:
         emit(line)
     if world > 1:
