@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SWR_ABI_VERSION 1
+#define SWR_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SWR_API __attribute__((visibility("default")))
@@ -158,6 +158,9 @@ typedef enum swr_op_kind {
   SWR_OP_BMV_BWD = 24,
   SWR_OP_BCE = 25,        /* BCELoss forward (mean) + d loss / d prediction (ctr_trainer.py:70) */
   SWR_OP_ADAM = 26,       /* torch.optim.Adam over flat param/grad/moment arenas (ctr_trainer.py:73) */
+  SWR_OP_FC_PRESPLIT = 27,/* effective weights W (.) W2 -> hi / lo TF32 images (both orientations) that the
+                             tcgen05 FC kernels read through TMA; sub-records = FC group records whose
+                             s[10] / s[11] name the forward / data-gradient image buffers           */
   SWR_OP_GROUP = 100      /* a group record belonging to the preceding header          */
 } swr_op_kind;
 

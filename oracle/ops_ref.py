@@ -590,6 +590,10 @@ class RefRunner:
                 dH.copy_(tot)
 
     # -- trainer-side ops (csrc/swr_train.cu) ---------------------------------------------------------------
+    def _op_27(self, h, subs):      # FC_PRESPLIT: weight images of the tcgen05 kernels; the interpreter reads the weights themselves
+        for r in subs:
+            assert int(r["s"][10]) >= 0 and int(r["s"][24]) >= 0
+
     def _op_25(self, h, subs):      # BCE
         B, ring = int(h["i"][0]), max(int(h["i"][2]), 1)
         p = self.slot(int(h["s"][0])).reshape(-1)[:B]

@@ -77,6 +77,7 @@ static FcGroup decode_fc(const swr_rec_t& r, Ctx& c) {
   g.dbias = static_cast<float*>(c.slot(r.s[30])); g.dbias2 = static_cast<float*>(c.slot(r.s[31]));
   g.w_layout = r.i[8]; g.ldw = r.i[9]; g.e_act = r.i[10]; g.flags = r.i[11]; g.e_scale = r.f[4];
   g.stats_out = (g.Y.norm.mode == SWR_NORM_BATCH) ? const_cast<double*>(g.Y.norm.stats) : nullptr;
+  g.img_f = static_cast<const float*>(c.slot(r.s[10])); g.img_d = static_cast<const float*>(c.slot(r.s[11]));
   return g;
 }
 
@@ -109,6 +110,14 @@ static int run_fc(int kind, const swr_rec_t* subs, int n, int64_t B, Ctx& c, cud
     if (rc) return rc;
   }
   return SWR_OK;
+}
+
+static int run_presplit(const swr_rec_t* subs, int n, Ctx& c, cudaStream_t st) {
+  if (fc_mode_get() == SWR_FC_SIMT) return SWR_OK;      // FFMA arithmetic reads the weights themselves
+  std::vector<FcGroup> groups(n);
+  for (int i = 0; i < n; ++i) groups[i] = decode_fc(subs[i], c);
+  if (!c.ok) return SWR_ERR_INVALID;
+  return launch_fc_presplit(groups.data(), n, st);
 }
 
 static int run_gather(const swr_rec_t& h, const swr_rec_t* subs, Ctx& c, cudaStream_t st) {
@@ -361,6 +370,7 @@ SWR_API int swr_program_run(const swr_rec_t* recs, int32_t n_recs, void* const* 
       case SWR_OP_COLSTATS:
         rc = launch_colstats(static_cast<const float*>(c.slot(h.s[0])), h.i[0], h.i[1], h.i[2], static_cast<double*>(c.slot(h.s[1])), st);
         break;
+      case SWR_OP_FC_PRESPLIT: rc = run_presplit(subs, h.n_sub, c, st); break;
       case SWR_OP_FC_FWD: case SWR_OP_FC_DGRAD: case SWR_OP_FC_WGRAD: rc = run_fc(h.kind, subs, h.n_sub, h.i[0], c, st); break;
       case SWR_OP_POOL_FWD: rc = run_pool(h, subs, false, c, st); break;
       case SWR_OP_POOL_BWD: rc = run_pool(h, subs, true, c, st); break;

@@ -718,6 +718,10 @@ int launch_fc_fwd(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t s
   if (B <= 0) return SWR_OK;
   int rc = check_groups(groups, n_groups, "fc_fwd");
   if (rc) return rc;
+  if (fc_tc_wanted(groups, n_groups, B) && fc_tc2_usable(groups, n_groups, 0)) {
+    rc = launch_fc_tc2_fwd(groups, n_groups, B, st);     // every group of the level, narrow ones included, in one launch
+    if (rc != SWR_ERR_UNSUPPORTED) return rc;
+  }
   if (fc_tc_wanted(groups, n_groups, B))
     return split_by_width(groups, n_groups, [&](const FcGroup* g, int n) { return launch_fc_tc_fwd(g, n, B, st); },
                           [&](const FcGroup* g, int n) { return skinny_ok(g, n) ? launch_fc_skinny_fwd(g, n, B, st) : launch_fc_fwd_simt(g, n, B, st); });
@@ -781,6 +785,10 @@ int launch_fc_dgrad(const FcGroup* groups, const int* dst_of, int n_groups, int6
   p.dst_group[n_dst] = n_groups;
   p.n_dst = n_dst;
   p.n_groups = n_groups; p.B = (int)B; p.inv_count = 1.0f / (float)B;
+  if (fc_tc_wanted(groups, n_groups, B) && fc_tc2_usable(groups, n_groups, 1)) {
+    rc = launch_fc_tc2_dgrad(groups, p.dst_group, n_dst, n_groups, B, st);
+    if (rc != SWR_ERR_UNSUPPORTED) return rc;
+  }
   if (fc_tc_wanted(groups, n_groups, B)) {
     rc = launch_fc_tc_dgrad(groups, p.dst_group, n_dst, n_groups, B, st);
     if (rc != SWR_ERR_UNSUPPORTED) return rc;   // else: a shape the tensor-core tiles cannot hold, FFMA serves it
@@ -818,6 +826,10 @@ int launch_fc_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t
   if (rc) return rc;
   for (int g = 0; g < n_groups; ++g)
     if (!groups[g].Y.dz) { set_error("fc_wgrad: group %d has no output gradient buffer", g); return SWR_ERR_INVALID; }
+  if (fc_tc_wanted(groups, n_groups, B) && fc_tc2_usable(groups, n_groups, 2)) {
+    rc = launch_fc_tc2_wgrad(groups, n_groups, B, st);
+    if (rc != SWR_ERR_UNSUPPORTED) return rc;
+  }
   if (fc_tc_wanted(groups, n_groups, B))
     return split_by_width(groups, n_groups, [&](const FcGroup* g, int n) { return launch_fc_tc_wgrad(g, n, B, st); },
                           [&](const FcGroup* g, int n) { return launch_fc_wgrad_simt(g, n, B, st); });

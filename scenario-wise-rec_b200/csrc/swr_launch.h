@@ -33,6 +33,8 @@ struct FcGroup {
   const float* bias; const float* bias2;  // effective bias = bias + bias2
   float* dW; float* dW2; float* dbias; float* dbias2;
   double* stats_out;    // [N][2] column moments of Y (train-mode BatchNorm), or null
+  const float* img_f;   // presplit weight images (swr_fc_tc2.cu): [2][N][K32] forward, [2][K][N32] data gradient; null = none
+  const float* img_d;
   int w_layout; int ldw;
   int e_act; float e_scale;   // epilogue activation for layers without a norm (GateNU)
   int flags;            // bit0: A needs a gradient, bit1: accumulate into A.dz
@@ -49,6 +51,13 @@ int fc_mode_set(int mode);
 int launch_fc_tc_fwd(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st);
 int launch_fc_tc_dgrad(const FcGroup* groups, const int* dst_group, int n_dst, int n_groups, int64_t B, cudaStream_t st);
 int launch_fc_tc_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st);
+// second-generation tcgen05 path (swr_fc_tc2.cu): TMA-fed presplit weights, persistent warp-specialised kernels.
+// pass: 0 forward, 1 data gradient, 2 weight gradient
+bool fc_tc2_usable(const FcGroup* groups, int n_groups, int pass);
+int launch_fc_presplit(const FcGroup* groups, int n_groups, cudaStream_t st);
+int launch_fc_tc2_fwd(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st);
+int launch_fc_tc2_dgrad(const FcGroup* groups, const int* dst_group, int n_dst, int n_groups, int64_t B, cudaStream_t st);
+int launch_fc_tc2_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st);
 
 // ---- row-local ops ----------------------------------------------------------------------
 constexpr int kMaxPoolExperts = 16;

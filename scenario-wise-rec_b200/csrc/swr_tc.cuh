@@ -2,10 +2,11 @@
 // mbarrier, TMEM allocation, tcgen05.mma (kind::tf32) issue, tcgen05.ld, and the shared-memory
 // operand layouts + matrix descriptors the MMA unit reads.
 //
-// Operand tiles are staged by the CTA's own threads (the operands are *computed* while staging:
-// lazy BatchNorm + activation, BatchNorm-backward affine map, STAR weight product, hi/lo TF32
-// split), so there is no TMA here; the tiles are written straight in the canonical 128-byte
-// swizzled layouts:
+// Weight tiles come through TMA (cp.async.bulk.tensor, SWIZZLE_128B) from images the presplit kernel wrote
+// (effective weight W (.) W2, hi/lo TF32 split, both orientations).  Activation-side operands are *computed*
+// while staging (lazy BatchNorm + activation, BatchNorm-backward affine map, hi/lo split) by stager warps and go
+// registers -> TMEM (tcgen05.st) or, for the weight-gradient's column operand, to shared memory in the same
+// canonical 128-byte swizzled layouts TMA produces:
 //   K-major  (contraction contiguous): row r (an M or N index) owns 128 B = 32 fp32 of contraction;
 //            16-byte chunk j of row r sits at r*128 + ((j ^ (r & 7)) << 4); 8 rows = one 1024 B atom.
 //            (SWIZZLE_128B, 16-byte base)
@@ -43,6 +44,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {   // one arrival + `bytes` of pending transactions
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -53,6 +57,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) __trap();
   }
+}
+
+// named barrier over a subset of the CTA's warps (id 1..15; `nthreads` a multiple of 32)
+__device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// ---- TMA ----------------------------------------------------------------------------------------
+// 3-D tiled load {c0 (innermost), c1, c2} of the box the tensor map was encoded with into shared memory; completion
+// is signalled on `bar` as transaction bytes.  `tmap` points at a CUtensorMap in kernel-parameter space
+// (__grid_constant__).
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_saddr, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst_saddr), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
 
 // ---- TMEM / tcgen05 ---------------------------------------------------------------------------
@@ -110,6 +130,13 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, float4 a, float4 b) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                ::"r"(taddr), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
+               : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
+                 "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
                : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }

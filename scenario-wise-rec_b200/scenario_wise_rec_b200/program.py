@@ -78,6 +78,8 @@ class _FcGroup:
     e_act: int = N.ACT_NONE
     e_scale: float = 1.0
     detach: bool = False            # no data gradient flows back into src (x.detach() in the reference)
+    img_f: int = -1                 # workspace slots of the presplit weight images the tcgen05 kernels read through TMA:
+    img_d: int = -1                 # [2][N][K32] (forward) and [2][K][N32] (data gradient), hi / lo TF32 planes
 
 
 @dataclass
@@ -379,6 +381,7 @@ class ProgramBuilder:
         s = r["s"]
         s[24], s[25], s[26], s[27] = self.static(g.W), self.static(g.W2), self.static(g.b), self.static(g.b2)
         s[28], s[29], s[30], s[31] = self.grad(g.W), self.grad(g.W2), self.grad(g.b), self.grad(g.b2)
+        s[10], s[11] = g.img_f, g.img_d
         r["i"][8], r["i"][9], r["i"][10], r["i"][11] = g.layout, int(g.W.stride(0)), g.e_act, flags
         r["f"][4] = g.e_scale
         return r
@@ -517,6 +520,18 @@ class ProgramBuilder:
             if op[0] == "mix":
                 mix_red[ti] = self.ws(2, f64=True)
                 dstat_slots.append(mix_red[ti])
+
+        # weight images for the tensor-core FC kernels: written by ONE presplit launch at the start of every forward
+        # (weights change between passes: optimizer steps, load_state_dict), read by the FC ops of both passes
+        fc_groups = [g for op in self.tape if op[0] == "fc" for g in op[1]]
+        for g in fc_groups:
+            n_out, k_in = g.out.n, g.src.n
+            g.img_f = self.ws(2 * n_out * _round_up(k_in, 32))
+            if self.training and g.src.needs_grad and not g.detach:
+                g.img_d = self.ws(2 * k_in * _round_up(n_out, 32))
+        if fc_groups:
+            fwd.append(self._hdr(N.OP_FC_PRESPLIT, len(fc_groups)))
+            fwd.extend(self._fc_rec(g) for g in fc_groups)
 
         # forward statistics: every f64 buffer allocated while building is a forward statistic -> one span
         f64_fwd = [self.slot_desc[s] for s in self._stats_slots]
