@@ -71,7 +71,9 @@ __device__ __forceinline__ ColCoef col_coef(const NormRef& nr, int c, float inv_
   if (nr.mode == SWR_NORM_NONE) { k.mu = 0.f; k.s = 1.f; k.b = 0.f; k.r = 1.f; return k; }
   double mu, var;
   col_moments(nr, c, inv_count, mu, var);
-  const float r = (float)(1.0 / sqrt(var + (double)nr.eps));
+  // the moments need fp64 (E[x^2] - E[x]^2); the reciprocal standard deviation does not: correctly rounded fp32 sqrt and
+  // divide (what the fp32 reference computes), a handful of instructions instead of a double-precision sqrt + divide
+  const float r = 1.0f / sqrtf((float)var + nr.eps);
   const float g = ld_opt(nr.gamma, c, 1.f) * ld_opt(nr.gamma2, c, 1.f);
   k.mu = (float)mu; k.r = r; k.s = g * r;
   k.b = ld_opt(nr.beta, c, 0.f) + ld_opt(nr.beta2, c, 0.f);
@@ -88,11 +90,12 @@ __device__ __forceinline__ DyCoef dy_coef(const ActDev& a, int c, float inv_coun
   const ColCoef k = col_coef(a.norm, c, inv_count);
   d.c0 = k.s;
   if (a.norm.mode == SWR_NORM_RUNNING) { d.c1 = 0.f; d.c2 = 0.f; return d; }
-  const double S1 = __ldcg(a.dstats + 2 * c), S2 = __ldcg(a.dstats + 2 * c + 1);
-  const double s = (double)k.s, r = (double)k.r, mu = (double)k.mu, ib = (double)inv_count * (double)a.norm.var_scale;
-  const double ib1 = (double)inv_count;
-  d.c1 = (float)(-s * r * S2 * ib);
-  d.c2 = (float)(-s * S1 * ib1 + s * r * S2 * mu * ib);
+  // the sums were reduced in fp64; the per-column coefficients are formed in fp32
+  const float S1 = (float)__ldcg(a.dstats + 2 * c), S2 = (float)__ldcg(a.dstats + 2 * c + 1);
+  const float ib = inv_count * a.norm.var_scale;
+  const float t = k.s * k.r * S2 * ib;
+  d.c1 = -t;
+  d.c2 = fmaf(t, k.mu, -k.s * S1 * inv_count);
   return d;
 }
 

@@ -78,6 +78,7 @@ static FcGroup decode_fc(const swr_rec_t& r, Ctx& c) {
   g.w_layout = r.i[8]; g.ldw = r.i[9]; g.e_act = r.i[10]; g.flags = r.i[11]; g.e_scale = r.f[4];
   g.stats_out = (g.Y.norm.mode == SWR_NORM_BATCH) ? const_cast<double*>(g.Y.norm.stats) : nullptr;
   g.img_f = static_cast<const float*>(c.slot(r.s[10])); g.img_d = static_cast<const float*>(c.slot(r.s[11]));
+  g.k_full = r.i[13] > 0 ? r.i[13] : g.A.n;
   return g;
 }
 

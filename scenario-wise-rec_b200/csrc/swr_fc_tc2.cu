@@ -3,17 +3,19 @@
 //
 // Same contract as the FFMA kernels in swr_fc.cu (fc_fwd / fc_dgrad / fc_wgrad over FcGroup lists; reference:
 // basic/layers.py:253-258 Linear -> BatchNorm1d -> act, star.py:103-110, ppnet.py:21-29, hamur.py adapters,
-// m3oe.py:45-68).  Arithmetic: 3xTF32 (x = hi + lo, three tcgen05.mma.kind::tf32 per k-step) as before.
+// m3oe.py:45-68).  Arithmetic: 3xTF32 (x = hi + lo, three tcgen05.mma.kind::tf32 per k-step).
 //
-// What changed against the first generation (swr_fc_tc_v1.cu):
 //   * Weights are split ONCE per forward pass by fc_presplit_kernel into "images": the effective weight
 //     W (.) W2 as hi / lo TF32 planes, in both orientations (contraction-contiguous for the forward and for
-//     the data gradient).  The kernels bring weight tiles in with cp.async.bulk.tensor (TMA, SWIZZLE_128B):
-//     no thread touches a weight any more.
-//   * Warp roles.  warps 0-7 stage the activation-side operand (lazy BatchNorm + activation, or the
-//     BatchNorm-backward affine map, + hi/lo split) from registers into TMEM (tcgen05.st); warps 8-15 are the
-//     epilogue; warp 16 lane 0 issues TMA; warp 17 lane 0 issues every tcgen05.mma.  Five mbarrier rings connect
-//     them (weight stage full, operand stage full, stage free, accumulator full, accumulator free).
+//     the data gradient).  Weight tiles arrive by TMA (cp.async.bulk.tensor, SWIZZLE_128B): no thread touches a weight.
+//   * The activation-side operands (activations, dz, raw outputs) also arrive by TMA, as RAW fp32 tiles; the stager
+//     warps read their rows from shared memory, apply the lazy BatchNorm + activation (forward), the BatchNorm-backward
+//     affine map (gradients) and the hi / lo split in registers, and write the MMA's row operand into TMEM
+//     (tcgen05.st).  No stager issues a global load: a thread-per-row global load touches 32 cache lines per
+//     instruction and was what bounded the first generation.
+//   * Warp roles: warps 0-7 stagers, warps 8-15 epilogue, warp 16 lane 0 issues every TMA, warp 17 lane 0 issues
+//     every tcgen05.mma.  mbarrier rings connect them: weight stages (TMA -> MMA), raw-tile stages (TMA -> stagers),
+//     TMEM operand stages (stagers -> MMA), accumulator buffers (MMA -> epilogue).
 //   * Persistent CTAs: each CTA walks a contiguous range of output tiles; two accumulator buffers in TMEM let
 //     the epilogue of one tile overlap the MMAs of the next.
 //   * Accumulator flushes.  tcgen05 accumulates with round-toward-zero, a bias that grows with the length of
@@ -37,36 +39,52 @@ constexpr int T2_NEPI = 8;                 // warps 8..15
 constexpr int T2_W_TMA = 16, T2_W_MMA = 17;
 constexpr int T2_THREADS = 18 * 32;
 constexpr int T2_MAX_STAGES = 4;
+constexpr int T2_ASTAGES = 4;              // TMEM operand stages
 constexpr uint32_t T2_ACC_COLS = 128;      // columns per accumulator buffer; buffers at TMEM columns 0 and 128
 constexpr uint32_t T2_A_COL0 = 256;        // TMEM-resident operand: stage s at columns 256 + 64 s (32 hi + 32 lo)
 constexpr uint32_t T2_TMEM_COLS = 512;
-constexpr int T2_OT_LD = 68;               // epilogue transpose tile: 128 rows x 64 columns (+4 pad)
-constexpr int T2_OT_BYTES = T2_BM * T2_OT_LD * 4;
-constexpr int T2_RED_BYTES = 2 * T2_NEPI * 64 * 8;
-constexpr int T2_BAR_STAGE = 1, T2_BAR_EPI = 2;   // named barriers of the stager / epilogue warps (256 threads each)
+constexpr int T2_RAW_BYTES = T2_BM * 128;  // one raw fp32 tile: 128 rows x 32 contraction elements (or 32 batch rows x 128 features)
+constexpr int T2_OT_LD = 36;               // epilogue transpose tile of one epilogue group: 128 rows x 32 columns (+4 pad)
+constexpr int T2_OT_GROUP = T2_BM * T2_OT_LD;       // floats per group
+constexpr int T2_OT_BYTES = 2 * T2_OT_GROUP * 4;
+constexpr int T2_RED_GROUP = 2 * 4 * 32;            // [2 statistics][4 warps][32 columns] floats per group
+constexpr int T2_RED_BYTES = 2 * T2_RED_GROUP * 4;
+// named barriers: stager warps (256 threads), all epilogue warps (256), one epilogue group (128 threads, id 3 + group)
+constexpr int T2_BAR_STAGE = 1, T2_BAR_EPI = 2, T2_BAR_EGRP = 3;
 enum { T2_FWD = 0, T2_DGRAD = 1 };
 
 struct alignas(64) Tc2Params {
-  CUtensorMap tm[kMaxGroups];      // weight image of group g for this pass (forward: img_f, data gradient: img_d)
+  CUtensorMap tm0[kMaxGroups];     // fwd: weight image img_f;  dgrad: weight image img_d;  wgrad: dz   [B, N] (box 128 x 32)
+  CUtensorMap tm1[kMaxGroups];     // fwd: input activation raw [B, K];  dgrad: dz [B, N];  wgrad: raw output [B, N]
+  CUtensorMap tm2[kMaxGroups];     // dgrad: raw output [B, N];  wgrad: input activation raw [B, K] (box NT x 32)
   FcGroup g[kMaxGroups];
   int tile_start[kMaxGroups + 1];  // fwd / wgrad: first tile of group g;  dgrad: first k-block of group g
   int nt[kMaxGroups];              // accumulator columns per tile: per group (fwd, wgrad) / per destination (dgrad)
   int n_groups, B;
   float inv_count;
-  int stages, flush, n_tiles;
-  int stage_bytes;                 // stride of the weight-stage ring (sized for the widest tile of the launch)
-  int off_coef, off_ccs, off_ot, off_red;   // shared-memory byte offsets (from the 1024-aligned base)
+  int sb, sr, flush, n_tiles;      // weight (wgrad: column-operand) stages, raw-tile stages
+  int stage_b, stage_r;            // bytes per stage of the two rings (sized for the widest tile of the launch)
+  int off_r, off_coef, off_ccs, off_ot, off_red;   // shared-memory byte offsets (from the 1024-aligned base); ring B at 0
   int n_dst;
   int dst_group[kMaxGroups + 1];
   int dst_tile[kMaxGroups + 1];
   unsigned dst_atomic;             // bit d: destination entry d is one of several partial fan-ins: add atomically
   int splits, rows_per_split;      // wgrad
+  int cluster;                     // fwd / dgrad: CTAs per cluster (1, 2 or 4) that share every weight tile by TMA multicast;
+                                   // a tile index then names `cluster` consecutive row tiles, one per CTA rank
+  long long* dbg;                  // development aid (SWR_TC_DEBUG): clock64 stamps of CTA 0, [role][128]; null in production
 };
 
+// development aid: event `i` of role `role` (0 TMA, 1 MMA, 2 stager warp 0, 3 epilogue warp 8) of CTA 0
+#define T2_STAMP(role, i) do { if (p.dbg && blockIdx.x == 0 && (i) < 128) p.dbg[(role) * 128 + (i)] = clock64(); } while (0)
+
 struct Tc2Shared {
-  uint64_t full_b[T2_MAX_STAGES];  // TMA landed the weight tile of the stage
-  uint64_t full_a[T2_MAX_STAGES];  // the stager warps wrote their operand(s) of the stage
-  uint64_t empty[T2_MAX_STAGES];   // tcgen05.commit: the MMAs that read the stage are done
+  uint64_t full_b[T2_MAX_STAGES];  // fwd/dgrad: TMA landed the weight tile
+  uint64_t empty_b[T2_MAX_STAGES]; // tcgen05.commit: the MMAs that read the stage are done
+  uint64_t full_r[T2_MAX_STAGES];  // TMA landed the raw tile(s)
+  uint64_t empty_r[T2_MAX_STAGES]; // the stager warps have consumed them
+  uint64_t full_a[T2_ASTAGES];     // the stager warps wrote the TMEM operand stage (wgrad: and the column-operand stage)
+  uint64_t empty_a[T2_ASTAGES];    // tcgen05.commit
   uint64_t acc_full[2];            // tcgen05.commit: a partial accumulator is complete
   uint64_t acc_empty[2];           // the epilogue warps have drained it
   uint32_t tmem_base;
@@ -94,7 +112,7 @@ struct T2Tile {
 };
 
 template <int MODE>
-__device__ __forceinline__ T2Tile t2_decode(const Tc2Params& p, int t) {
+__device__ __forceinline__ T2Tile t2_decode(const Tc2Params& p, int t, int rank) {
   T2Tile T{};
   if (MODE == T2_FWD) {
     int g = 0;
@@ -102,7 +120,7 @@ __device__ __forceinline__ T2Tile t2_decode(const Tc2Params& p, int t) {
     const int N = p.g[g].Y.n, K = p.g[g].A.n;
     T.g = g; T.NT = p.nt[g];
     const int nt_n = (N + T.NT - 1) / T.NT, local = t - p.tile_start[g];
-    T.m0 = (local / nt_n) * T2_BM; T.n0 = (local % nt_n) * T.NT;
+    T.m0 = ((local / nt_n) * p.cluster + rank) * T2_BM; T.n0 = (local % nt_n) * T.NT;
     T.nkb = (K + KBLK - 1) / KBLK;
   } else {
     int d = 0;
@@ -111,7 +129,7 @@ __device__ __forceinline__ T2Tile t2_decode(const Tc2Params& p, int t) {
     const int Kd = p.g[T.g].A.n;
     T.NT = p.nt[d];
     const int nt_n = (Kd + T.NT - 1) / T.NT, local = t - p.dst_tile[d];
-    T.m0 = (local / nt_n) * T2_BM; T.n0 = (local % nt_n) * T.NT;
+    T.m0 = ((local / nt_n) * p.cluster + rank) * T2_BM; T.n0 = (local % nt_n) * T.NT;
     T.kb0 = p.tile_start[T.g];
     T.nkb = p.tile_start[T.ge] - T.kb0;
   }
@@ -132,20 +150,26 @@ __device__ __forceinline__ void t2_issue(uint32_t d_tmem, uint32_t a_tmem, uint3
   }
 }
 
-__device__ __forceinline__ void t2_setup(Tc2Shared& sh, int S, int tid, int warp) {
+__device__ __forceinline__ void t2_setup(Tc2Shared& sh, int tid, int warp, int stager_arrivals, int cluster) {
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&sh.full_b[s], 1); mbar_init(&sh.full_a[s], T2_NSTAGER); mbar_init(&sh.empty[s], 1); }
+    for (int s = 0; s < T2_MAX_STAGES; ++s) {
+      mbar_init(&sh.full_b[s], 1); mbar_init(&sh.empty_b[s], cluster);   // every CTA of the cluster releases a multicast stage
+      mbar_init(&sh.full_r[s], 1); mbar_init(&sh.empty_r[s], stager_arrivals);
+    }
+    for (int s = 0; s < T2_ASTAGES; ++s) { mbar_init(&sh.full_a[s], stager_arrivals); mbar_init(&sh.empty_a[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&sh.acc_full[b], 1); mbar_init(&sh.acc_empty[b], T2_NEPI); }
     fence_mbar_init();
   }
   if (warp == T2_W_MMA) tmem_alloc(&sh.tmem_base, T2_TMEM_COLS);
   fence_before_sync();
   __syncthreads();
+  if (cluster > 1) cluster_sync_all();     // peers signal our barriers and write our stages: they must be initialised first
   fence_after_sync();
 }
 
-__device__ __forceinline__ void t2_range(int n_tiles, int& t_begin, int& t_end) {
-  const int per = n_tiles / (int)gridDim.x, rem = n_tiles % (int)gridDim.x, b = (int)blockIdx.x;
+__device__ __forceinline__ void t2_range(int n_tiles, int cluster, int& t_begin, int& t_end) {
+  const int nb = (int)gridDim.x / cluster, b = (int)blockIdx.x / cluster;
+  const int per = n_tiles / nb, rem = n_tiles % nb;
   t_begin = b * per + min(b, rem);
   t_end = t_begin + per + (b < rem ? 1 : 0);
 }
@@ -155,17 +179,7 @@ __device__ __forceinline__ float4 t2_zero4() { return make_float4(0.f, 0.f, 0.f,
 __device__ __forceinline__ void t2_red_add_v4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
-// 4 floats at p (16-byte aligned, readable), components >= nvalid zeroed
-__device__ __forceinline__ float4 t2_ld4_mask(const float* p, int nvalid) {
-  if (nvalid <= 0) return t2_zero4();
-  float4 v = __ldg(reinterpret_cast<const float4*>(p));
-  if (nvalid < 4) { v.w = 0.f; if (nvalid < 3) v.z = 0.f; if (nvalid < 2) v.y = 0.f; }
-  return v;
-}
 __device__ __forceinline__ float t2_slope(int act) { return act == SWR_ACT_RELU ? 0.f : (act == SWR_ACT_LEAKY ? 0.1f : 1.f); }
-__device__ __forceinline__ float t2_act(float z, float slope, bool sig) {
-  return sig ? 1.f / (1.f + expf(-z)) : fmaxf(z, slope * z);
-}
 
 // split 16 values and store them as this thread's 16 hi + 16 lo columns of an operand stage
 __device__ __forceinline__ void t2_store_split16(uint32_t taddr_hi, const float (&v)[16]) {
@@ -175,38 +189,63 @@ __device__ __forceinline__ void t2_store_split16(uint32_t taddr_hi, const float 
   tmem_st16(taddr_hi, hi);
   tmem_st16(taddr_hi + 32, lo);
 }
+// same for elements [o, o + 16) of a 32-element row
+__device__ __forceinline__ void t2_store_split16(uint32_t taddr_hi, const float (&v)[32], int o) {
+  float hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) split_tf32(v[o + i], hi[i], lo[i]);
+  tmem_st16(taddr_hi, hi);
+  tmem_st16(taddr_hi + 32, lo);
+}
+__device__ __noinline__ float4 t2_sigmoid4(float4 z) {
+  return make_float4(1.f / (1.f + expf(-z.x)), 1.f / (1.f + expf(-z.y)), 1.f / (1.f + expf(-z.z)), 1.f / (1.f + expf(-z.w)));
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+// this thread's 16 contraction elements of row `row` (chunks 4 kh .. 4 kh + 3) of a K-major swizzled raw tile
+__device__ __forceinline__ void t2_lds_row16(const uint8_t* tile, int row, int kh, float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 x = *reinterpret_cast<const float4*>(tile + kmajor_off(row, 4 * kh + i));
+    v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+  }
+}
 
 // ---- epilogue helpers -------------------------------------------------------------------------------------
-// drain this warp's share (lane quarter q, columns [64 ch, 64 ch + 64) of an NT-wide accumulator) and add it to acc
+// drain this warp's share (lane quarter q, columns [64 ch, 64 ch + 64) of an NT-wide accumulator) and add it to acc.
+// Eight columns per load: the running sums already take 64 registers of a 96-register budget, and a spilled register
+// costs an L2 round trip here (the shared-memory carve-out leaves no L1).
 __device__ __forceinline__ void t2_drain_add(uint32_t tmem_acc, int q, int ch, int NT, float (&acc)[64]) {
-  const int my = min(max(NT - 64 * ch, 0), 64);
+  const int my = min(max(NT - 64 * ch, 0), 64);       // 0, 16, 32, 48 or 64 columns (warp-uniform)
   const uint32_t taddr = tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)(64 * ch);
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    if (16 * c < my) {      // warp-uniform
-      uint32_t r[16];
-      tmem_ld16(taddr + 16 * c, r);
+  for (int c = 0; c < 8; ++c) {
+    if (8 * c < my) {
+      uint32_t r[8];
+      tmem_ld8(taddr + 8 * c, r);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[16 * c + i] += __uint_as_float(r[i]);
+      for (int i = 0; i < 8; ++i) acc[8 * c + i] += __uint_as_float(r[i]);
     }
   }
 }
-// the partial sums of the warps that own column half `pass` -> ot[128][T2_OT_LD]
-__device__ __forceinline__ void t2_acc_to_smem(float* ot, int row, int pc, const float (&acc)[64]) {
+// 32 accumulator columns [32 sp, 32 sp + 32) of this thread's row -> the group's transpose tile (shared-space address)
+__device__ __forceinline__ void t2_acc_to_smem(uint32_t ot_s, int row, int sp, int pc, const float (&acc)[64]) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i)
-    if (4 * i < pc) *reinterpret_cast<float4*>(ot + (size_t)row * T2_OT_LD + 4 * i) = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+  for (int i = 0; i < 8; ++i)
+    if (4 * i < pc) {
+      const float4 v = sp == 0 ? make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3])
+                               : make_float4(acc[32 + 4 * i], acc[32 + 4 * i + 1], acc[32 + 4 * i + 2], acc[32 + 4 * i + 3]);
+      sts128(ot_s + (uint32_t)(row * T2_OT_LD + 4 * i) * 4u, v);
+    }
 }
-// red: [2][T2_NEPI][64] doubles -> one fp64 atomic per column and statistic
-__device__ __forceinline__ void t2_col_atomics(const double* red, double* gstats, int col0, int nvalid, int etid) {
-  for (int i = etid; i < 2 * nvalid; i += 32 * T2_NEPI) {
-    const int which = i / nvalid, col = i - which * nvalid;
-    double t = 0.0;
-#pragma unroll
-    for (int w = 0; w < T2_NEPI; ++w) t += red[(which * T2_NEPI + w) * 64 + col];
-    atomicAdd(gstats + 2 * (col0 + col) + which, t);
-  }
+// forward epilogue value of one accumulator element: bias, optional activation of layers without a norm (GateNU)
+__device__ __forceinline__ float t2_epi_val(float a, float bias, int e_act, float e_scale) {
+  const float y = a + bias;
+  return e_act == SWR_ACT_NONE ? y : act_fwd(y, e_act) * e_scale;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -221,264 +260,352 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
   uint8_t* smem = t2_align1024(smem_raw);
   const uint32_t smem_s = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int S = p.stages, F = p.flush, M = p.B;
+  const int SB = p.sb, SR = p.sr, F = p.flush, M = p.B;
   int t_begin, t_end;
-  t2_range(p.n_tiles, t_begin, t_end);
-  t2_setup(sh, S, tid, warp);
+  const int C = p.cluster, crank = C > 1 ? (int)cluster_ctarank() : 0;
+  t2_range(p.n_tiles, C, t_begin, t_end);
+  if (tid == 0) T2_STAMP(0, 126);
+  t2_setup(sh, tid, warp, T2_NSTAGER / 2, C);
   const uint32_t tmem = sh.tmem_base;
+  if (tid == 0) T2_STAMP(0, 127);
 
   if (warp == T2_W_TMA) {
-    // ===== TMA producer: weight tiles =====
-    if (lane == 0) {
-      T2Ring r; r.init();
-      for (int t = t_begin; t < t_end; ++t) {
-        const T2Tile T = t2_decode<MODE>(p, t);
-        const uint32_t bytes = 2u * (uint32_t)T.NT * 128u, stage_bytes = (uint32_t)p.stage_bytes;
-        if (MODE == T2_FWD) {
-          for (int kb = 0; kb < T.nkb; ++kb, r.next(S)) {
-            mbar_wait(&sh.empty[r.s], r.ph ^ 1u);
-            mbar_expect_tx(&sh.full_b[r.s], bytes);
-            tma_load_3d(smem_s + (uint32_t)r.s * stage_bytes, &p.tm[T.g], kb * KBLK, T.n0, 0, &sh.full_b[r.s]);
-          }
-        } else {
-          for (int g = T.g; g < T.ge; ++g) {
-            const int nk = p.tile_start[g + 1] - p.tile_start[g];
-            for (int kb = 0; kb < nk; ++kb, r.next(S)) {
-              mbar_wait(&sh.empty[r.s], r.ph ^ 1u);
-              mbar_expect_tx(&sh.full_b[r.s], bytes);
-              tma_load_3d(smem_s + (uint32_t)r.s * stage_bytes, &p.tm[g], kb * KBLK, T.n0, 0, &sh.full_b[r.s]);
-            }
+    // ===== TMA producer: weight tiles (ring B) and raw activation-side tiles (ring R) =====
+    // The whole warp walks the loop (so every operand is warp-uniform); one elected lane issues.  The two rings
+    // advance independently: raw tiles feed the longer chain (stagers -> TMEM -> MMA) and run ahead as far as their
+    // ring allows; a cursor is a (tile, group, k-block) position in the CTA's k-block sequence.
+    struct Cursor { int t, g, ge, kb, nk, m0, n0, NT; T2Ring r; bool done; };
+    auto enter = [&](Cursor& c) {
+      const T2Tile T = t2_decode<MODE>(p, c.t, crank);
+      c.g = T.g; c.ge = T.ge; c.m0 = T.m0; c.n0 = T.n0; c.NT = T.NT; c.kb = 0;
+      c.nk = (MODE == T2_FWD) ? T.nkb : p.tile_start[c.g + 1] - p.tile_start[c.g];
+    };
+    auto start = [&](Cursor& c) {
+      c.t = t_begin; c.done = (t_begin >= t_end); c.r.init();
+      if (!c.done) enter(c);
+    };
+    auto advance = [&](Cursor& c, int S) {
+      c.r.next(S);
+      if (++c.kb < c.nk) return;
+      c.kb = 0;
+      if (MODE == T2_DGRAD && ++c.g < c.ge) { c.nk = p.tile_start[c.g + 1] - p.tile_start[c.g]; return; }
+      if (++c.t >= t_end) { c.done = true; return; }
+      enter(c);
+    };
+    Cursor cb, cr;
+    start(cb); start(cr);
+    int ev = 0;
+    while (!cb.done || !cr.done) {
+      // raw tiles first; block on a ring only when the other one has nothing to issue either
+      const bool r_ready = !cr.done && mbar_test(&sh.empty_r[cr.r.s], cr.r.ph ^ 1u);
+      const bool b_ready = !cb.done && mbar_test(&sh.empty_b[cb.r.s], cb.r.ph ^ 1u);
+      if (!r_ready && !b_ready) {
+        if (!cr.done) mbar_wait(&sh.empty_r[cr.r.s], cr.r.ph ^ 1u);
+        else mbar_wait(&sh.empty_b[cb.r.s], cb.r.ph ^ 1u);
+        continue;
+      }
+      if (r_ready) {
+        const bool two = (MODE == T2_DGRAD) && (p.g[cr.g].Y.norm.mode == SWR_NORM_BATCH);
+        if (elect_one()) {
+          mbar_expect_tx(&sh.full_r[cr.r.s], two ? 2u * T2_RAW_BYTES : (uint32_t)T2_RAW_BYTES);
+          const uint32_t rdst = smem_s + (uint32_t)(p.off_r + cr.r.s * p.stage_r);
+          tma_load_2d(rdst, &p.tm1[cr.g], cr.kb * KBLK, cr.m0, &sh.full_r[cr.r.s]);
+          if (two) tma_load_2d(rdst + T2_RAW_BYTES, &p.tm2[cr.g], cr.kb * KBLK, cr.m0, &sh.full_r[cr.r.s]);
+        }
+        __syncwarp();
+        advance(cr, SR);
+      }
+      if (b_ready) {
+        if (elect_one()) {
+          mbar_expect_tx(&sh.full_b[cb.r.s], 2u * (uint32_t)cb.NT * 128u);
+          const uint32_t bdst = smem_s + (uint32_t)(cb.r.s * p.stage_b);
+          if (C == 1) {
+            tma_load_3d(bdst, &p.tm0[cb.g], cb.kb * KBLK, cb.n0, 0, &sh.full_b[cb.r.s]);
+          } else {      // this CTA fetches rows [crank, crank + 1) * NT / C of both planes for every CTA of the cluster
+            const int rows = cb.NT / C;
+            const uint32_t so = (uint32_t)(crank * rows) * 128u;
+            const uint16_t mask = (uint16_t)((1u << C) - 1u);
+            tma_load_3d_mc(bdst + so, &p.tm0[cb.g], cb.kb * KBLK, cb.n0 + crank * rows, 0, &sh.full_b[cb.r.s], mask);
+            tma_load_3d_mc(bdst + (uint32_t)cb.NT * 128u + so, &p.tm0[cb.g], cb.kb * KBLK, cb.n0 + crank * rows, 1, &sh.full_b[cb.r.s], mask);
           }
         }
+        __syncwarp();
+        if (lane == 0) { T2_STAMP(0, ev); } ++ev;
+        advance(cb, SB);
       }
     }
   } else if (warp == T2_W_MMA) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      T2Ring r; r.init();
+    // ===== MMA issuer: converged warp, one elected lane issues the tcgen05.mma / commit instructions =====
+    {
+      T2Ring rb, ra; rb.init(); ra.init();
       uint32_t acc_it = 0;
+      int ev = 0;
       for (int t = t_begin; t < t_end; ++t) {
-        const T2Tile T = t2_decode<MODE>(p, t);
-        const uint32_t b_bytes = (uint32_t)T.NT * 128u, stage_bytes = (uint32_t)p.stage_bytes;
+        const T2Tile T = t2_decode<MODE>(p, t, crank);
+        const uint32_t b_bytes = (uint32_t)T.NT * 128u;
         const uint32_t idesc = make_idesc_tf32(T2_BM, T.NT, false, false);
         int fpos = 0;
-        for (int kb = 0; kb < T.nkb; ++kb, r.next(S)) {
+        for (int kb = 0; kb < T.nkb; ++kb, rb.next(SB), ra.next(T2_ASTAGES)) {
           const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
-          if (fpos == 0) { mbar_wait(&sh.acc_empty[buf], aph ^ 1u); fence_after_sync(); }
-          mbar_wait(&sh.full_b[r.s], r.ph);
-          mbar_wait(&sh.full_a[r.s], r.ph);
+          if (fpos == 0) mbar_wait(&sh.acc_empty[buf], aph ^ 1u);
+          mbar_wait(&sh.full_b[rb.s], rb.ph);
+          mbar_wait(&sh.full_a[ra.s], ra.ph);
           fence_after_sync();
-          t2_issue(tmem + buf * T2_ACC_COLS, tmem + T2_A_COL0 + (uint32_t)r.s * 64u, smem_s + (uint32_t)r.s * stage_bytes, b_bytes,
-                   false, idesc, fpos == 0);
-          mma_commit(&sh.empty[r.s]);
-          if (++fpos == F || kb == T.nkb - 1) { mma_commit(&sh.acc_full[buf]); ++acc_it; fpos = 0; }
+          const bool last = (fpos + 1 == F) || (kb == T.nkb - 1);
+          if (elect_one()) {
+            t2_issue(tmem + buf * T2_ACC_COLS, tmem + T2_A_COL0 + (uint32_t)ra.s * 64u, smem_s + (uint32_t)(rb.s * p.stage_b), b_bytes,
+                     false, idesc, fpos == 0);
+            if (C == 1) mma_commit(&sh.empty_b[rb.s]); else mma_commit_mc(&sh.empty_b[rb.s], (uint16_t)((1u << C) - 1u));
+            mma_commit(&sh.empty_a[ra.s]);
+            if (last) mma_commit(&sh.acc_full[buf]);
+          }
+          __syncwarp();
+          if (last) { ++acc_it; fpos = 0; } else ++fpos;
+          if (lane == 0) { T2_STAMP(1, ev); } ++ev;
         }
       }
     }
   } else if (warp < T2_NSTAGER) {
-    // ===== stagers: the 128-row operand, registers -> TMEM =====
-    const int q = warp & 3, kh = warp >> 2, stid = tid;          // lane quarter, half of the k-block, 0..255
+    // ===== stagers: raw tile (shared memory) -> transform -> split -> TMEM =====
+    // Two groups of four warps (one warp per TMEM lane quarter) alternate over the k-blocks of the CTA, so that the
+    // handshake latencies of consecutive k-blocks overlap; a thread stages the 32 contraction elements of its row.
+    const int q = warp & 3, grp = warp >> 2, stid = tid;
     const int row = 32 * q + lane;
-    const uint32_t ta = tmem + T2_A_COL0 + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * kh);
+    const uint32_t ta = tmem + T2_A_COL0 + ((uint32_t)(32 * q) << 16);
     float* coef = reinterpret_cast<float*>(smem + p.off_coef);
-    T2Ring r; r.init();
-    int cur_key = -1;
+    T2Ring rr, ra; rr.init(); ra.init();
+    if (grp) { rr.next(SR); ra.next(T2_ASTAGES); }
+    int kbg = 0, cur_key = -1, ev = 0;     // kbg: k-blocks of the CTA before this tile (its parity picks the group)
     for (int t = t_begin; t < t_end; ++t) {
-      const T2Tile T = t2_decode<MODE>(p, t);
-      const int mrow = min(T.m0 + row, M - 1);      // rows past the batch only feed accumulator rows that are never stored
+      const T2Tile T = t2_decode<MODE>(p, t, crank);
+      const int Kc = T.nkb * KBLK;         // padded contraction length of the tile (fwd: K; dgrad: the whole fan-in)
+      bool plainA = false, sig = false;
+      float slope = 1.f;
       if (MODE == T2_FWD) {
         const FcGroup& G = p.g[T.g];
-        const int K = G.A.n, Kpad = T.nkb * KBLK;
-        const bool plainA = (G.A.norm.mode == SWR_NORM_NONE && G.A.act == SWR_ACT_NONE);
-        if (!plainA && cur_key != T.g) {            // [3][Kpad]: mu, s, b of the input columns (zero beyond K)
+        const int K = G.A.n;
+        plainA = (G.A.norm.mode == SWR_NORM_NONE && G.A.act == SWR_ACT_NONE);
+        slope = t2_slope(G.A.act); sig = G.A.act == SWR_ACT_SIGMOID;
+        if (!plainA && cur_key != T.g) {            // [3][Kc]: mu, s, b of the input columns (zero beyond K)
           named_bar(T2_BAR_STAGE, 32 * T2_NSTAGER);
-          for (int k = stid; k < Kpad; k += 32 * T2_NSTAGER) {
+          for (int k = stid; k < Kc; k += 32 * T2_NSTAGER) {
             ColCoef c = {0.f, 0.f, 0.f, 0.f};
             if (k < K) c = col_coef(G.A.norm, k, p.inv_count);
-            coef[k] = c.mu; coef[Kpad + k] = c.s; coef[2 * Kpad + k] = c.b;
+            coef[k] = c.mu; coef[Kc + k] = c.s; coef[2 * Kc + k] = c.b;
           }
           named_bar(T2_BAR_STAGE, 32 * T2_NSTAGER);
           cur_key = T.g;
         }
-        const float slope = t2_slope(G.A.act);
-        const bool sig = G.A.act == SWR_ACT_SIGMOID;
-        const float* src = G.A.raw + (int64_t)mrow * G.A.ld + 16 * kh;
-        float4 x[4];
-        auto load = [&](int kb) {
-          const int k = kb * KBLK + 16 * kh;
+      } else if (cur_key != T.d) {
+        // coefficients of dY = c0 * dz + c1 * raw + c2 over the concatenated output columns of the fan-in
+        named_bar(T2_BAR_STAGE, 32 * T2_NSTAGER);
+        for (int g = T.g; g < T.ge; ++g) {
+          const FcGroup& G = p.g[g];
+          const int base = (p.tile_start[g] - T.kb0) * KBLK, span = (p.tile_start[g + 1] - p.tile_start[g]) * KBLK;
+          for (int n = stid; n < span; n += 32 * T2_NSTAGER) {
+            DyCoef c = {0.f, 0.f, 0.f};
+            if (n < G.Y.n) c = dy_coef(G.Y, n, p.inv_count);
+            coef[base + n] = c.c0; coef[Kc + base + n] = c.c1; coef[2 * Kc + base + n] = c.c2;
+          }
+        }
+        named_bar(T2_BAR_STAGE, 32 * T2_NSTAGER);
+        cur_key = T.d;
+      }
+      int g = T.g, g_end_kb = (MODE == T2_DGRAD) ? p.tile_start[T.g + 1] - T.kb0 : T.nkb;
+      bool two = (MODE == T2_DGRAD) && p.g[g].Y.norm.mode == SWR_NORM_BATCH;
+      for (int kb = 0; kb < T.nkb; ++kb) {
+        if (MODE == T2_DGRAD) {
+          while (kb >= g_end_kb) { ++g; g_end_kb = p.tile_start[g + 1] - T.kb0; two = p.g[g].Y.norm.mode == SWR_NORM_BATCH; }
+        }
+        if (((kbg + kb) & 1) != grp) continue;
+        mbar_wait(&sh.full_r[rr.s], rr.ph);
+        mbar_wait(&sh.empty_a[ra.s], ra.ph ^ 1u);
+        fence_after_sync();
+        if (tid == 0) { T2_STAMP(2, ev); ++ev; }
+        const uint32_t rt = smem_s + (uint32_t)(p.off_r + rr.s * p.stage_r);
+        const uint32_t tst = ta + (uint32_t)ra.s * 64u;
+        const float* c = coef + kb * KBLK;
+        // two halves of 16 contraction elements, each taken from shared memory to TMEM before the next one starts
+        // (keeps the live registers of the loop near 60)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) x[i] = t2_ld4_mask(src + kb * KBLK + 4 * i, K - (k + 4 * i));
-        };
-        load(0);
-        for (int kb = 0; kb < T.nkb; ++kb, r.next(S)) {
-          mbar_wait(&sh.empty[r.s], r.ph ^ 1u);
-          fence_after_sync();
+        for (int h = 0; h < 2; ++h) {
           float v[16];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { v[4 * i] = x[i].x; v[4 * i + 1] = x[i].y; v[4 * i + 2] = x[i].z; v[4 * i + 3] = x[i].w; }
-          if (!plainA) {
-            const float* c = coef + kb * KBLK + 16 * kh;
+          for (int i = 0; i < 4; ++i) {
+            const float4 x = lds128(rt + kmajor_off(row, 4 * h + i));
+            v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+          }
+          const float* ch_ = c + 16 * h;
+          if (MODE == T2_FWD) {
+            if (!plainA) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 mu = t2_ld4s(ch_ + 4 * i), sc = t2_ld4s(ch_ + Kc + 4 * i), bb = t2_ld4s(ch_ + 2 * Kc + 4 * i);
+                v[4 * i] = fmaf(v[4 * i] - mu.x, sc.x, bb.x); v[4 * i + 1] = fmaf(v[4 * i + 1] - mu.y, sc.y, bb.y);
+                v[4 * i + 2] = fmaf(v[4 * i + 2] - mu.z, sc.z, bb.z); v[4 * i + 3] = fmaf(v[4 * i + 3] - mu.w, sc.w, bb.w);
+              }
+              if (sig) {          // rare as an input activation: out of line, four values per call
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float4 y = t2_sigmoid4(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+                  v[4 * i] = y.x; v[4 * i + 1] = y.y; v[4 * i + 2] = y.z; v[4 * i + 3] = y.w;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], slope * v[i]);
+              }
+            }
+          } else if (two) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 mu = t2_ld4s(c + 4 * i), sc = t2_ld4s(c + Kpad + 4 * i), bb = t2_ld4s(c + 2 * Kpad + 4 * i);
-              v[4 * i] = t2_act(fmaf(v[4 * i] - mu.x, sc.x, bb.x), slope, sig);
-              v[4 * i + 1] = t2_act(fmaf(v[4 * i + 1] - mu.y, sc.y, bb.y), slope, sig);
-              v[4 * i + 2] = t2_act(fmaf(v[4 * i + 2] - mu.z, sc.z, bb.z), slope, sig);
-              v[4 * i + 3] = t2_act(fmaf(v[4 * i + 3] - mu.w, sc.w, bb.w), slope, sig);
+              const float4 w = lds128(rt + T2_RAW_BYTES + kmajor_off(row, 4 * h + i));
+              const float4 c0 = t2_ld4s(ch_ + 4 * i), c1 = t2_ld4s(ch_ + Kc + 4 * i), c2 = t2_ld4s(ch_ + 2 * Kc + 4 * i);
+              v[4 * i] = fmaf(c0.x, v[4 * i], fmaf(c1.x, w.x, c2.x)); v[4 * i + 1] = fmaf(c0.y, v[4 * i + 1], fmaf(c1.y, w.y, c2.y));
+              v[4 * i + 2] = fmaf(c0.z, v[4 * i + 2], fmaf(c1.z, w.z, c2.z)); v[4 * i + 3] = fmaf(c0.w, v[4 * i + 3], fmaf(c1.w, w.w, c2.w));
             }
-          }
-          t2_store_split16(ta + (uint32_t)r.s * 64u, v);
-          if (kb + 1 < T.nkb) load(kb + 1);
-          tmem_st_wait();
-          fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sh.full_a[r.s]);
-        }
-      } else {
-        // coefficients of dY = c0 * dz + c1 * raw + c2 over the concatenated output columns of the fan-in
-        const int Kc = T.nkb * KBLK;
-        if (cur_key != T.d) {
-          named_bar(T2_BAR_STAGE, 32 * T2_NSTAGER);
-          for (int g = T.g; g < T.ge; ++g) {
-            const FcGroup& G = p.g[g];
-            const int base = (p.tile_start[g] - T.kb0) * KBLK, span = (p.tile_start[g + 1] - p.tile_start[g]) * KBLK;
-            for (int n = stid; n < span; n += 32 * T2_NSTAGER) {
-              DyCoef c = {0.f, 0.f, 0.f};
-              if (n < G.Y.n) c = dy_coef(G.Y, n, p.inv_count);
-              coef[base + n] = c.c0; coef[Kc + base + n] = c.c1; coef[2 * Kc + base + n] = c.c2;
-            }
-          }
-          named_bar(T2_BAR_STAGE, 32 * T2_NSTAGER);
-          cur_key = T.d;
-        }
-        int g = T.g, g_kb0 = 0, g_nk = p.tile_start[T.g + 1] - p.tile_start[T.g];
-        float4 x[4], w[4];
-        // (group, k-block inside it) of the tile's k-block kb; advances g monotonically
-        auto load = [&](int kb) {
-          while (kb >= g_kb0 + g_nk) { g_kb0 += g_nk; ++g; g_nk = p.tile_start[g + 1] - p.tile_start[g]; }
-          const FcGroup& G = p.g[g];
-          const int lk = (kb - g_kb0) * KBLK + 16 * kh, N = G.Y.n;
-          const int64_t o = (int64_t)mrow * G.Y.ld + lk;
-          const bool need_raw = (G.Y.norm.mode == SWR_NORM_BATCH);
+          } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            x[i] = t2_ld4_mask(G.Y.dz + o + 4 * i, N - (lk + 4 * i));
-            w[i] = need_raw ? t2_ld4_mask(G.Y.raw + o + 4 * i, N - (lk + 4 * i)) : t2_zero4();
+            for (int i = 0; i < 4; ++i) {
+              const float4 c0 = t2_ld4s(ch_ + 4 * i), c2 = t2_ld4s(ch_ + 2 * Kc + 4 * i);
+              v[4 * i] = fmaf(c0.x, v[4 * i], c2.x); v[4 * i + 1] = fmaf(c0.y, v[4 * i + 1], c2.y);
+              v[4 * i + 2] = fmaf(c0.z, v[4 * i + 2], c2.z); v[4 * i + 3] = fmaf(c0.w, v[4 * i + 3], c2.w);
+            }
           }
-        };
-        load(0);
-        for (int kb = 0; kb < T.nkb; ++kb, r.next(S)) {
-          mbar_wait(&sh.empty[r.s], r.ph ^ 1u);
+          t2_store_split16(tst + 16 * h, v);
+          asm volatile("" ::: "memory");
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.empty_r[rr.s]);   // every lane's values left shared memory before its split
+        tmem_st_wait();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.full_a[ra.s]);
+        if (tid == 0) { T2_STAMP(2, ev); ++ev; }
+        rr.next(SR); rr.next(SR); ra.next(T2_ASTAGES); ra.next(T2_ASTAGES);
+      }
+      kbg += T.nkb;
+    }
+  } else if (warp < T2_NSTAGER + T2_NEPI) {
+    // ===== epilogue warps =====
+    // Two independent groups of four warps (one per TMEM lane quarter): group ch owns accumulator columns
+    // [64 ch, 64 ch + 64), drains them into registers flush by flush, then finishes them in two 32-column passes
+    // through its own transpose tile (so the registers of a pass are dead before its row loop runs).
+    const int e = warp - T2_NSTAGER, q = warp & 3, ch = e >> 2;
+    uint32_t acc_it = 0;
+    int ev3 = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      float acc[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+      {
+        // Only what the drain loop needs is decoded here: the running sums take 64 of the 96 registers, and a spilled
+        // register is an L2 round trip (the shared-memory carve-out leaves no L1).  The tile is decoded again below.
+        const T2Tile T0 = t2_decode<MODE>(p, t, crank);
+        if (MODE == T2_DGRAD) {
+          // coefficients of the destination's own norm / activation: [4][NT] mu, s, b, r
+          const ActDev& D0 = p.g[T0.g].A;
+          const bool plain0 = D0.norm.mode == SWR_NORM_NONE && D0.act == SWR_ACT_NONE;
+          const int Nend0 = min(D0.n, T0.n0 + T0.NT);
+          float* ccs0 = reinterpret_cast<float*>(smem + p.off_ccs);
+          named_bar(T2_BAR_EPI, 32 * T2_NEPI);
+          for (int c = tid - 32 * T2_NSTAGER; c < T0.NT; c += 32 * T2_NEPI) {
+            ColCoef cc = {0.f, 1.f, 0.f, 1.f};
+            if (!plain0 && T0.n0 + c < Nend0) cc = col_coef(D0.norm, T0.n0 + c, p.inv_count);
+            ccs0[c] = cc.mu; ccs0[T0.NT + c] = cc.s; ccs0[2 * T0.NT + c] = cc.b; ccs0[3 * T0.NT + c] = cc.r;
+          }
+          named_bar(T2_BAR_EPI, 32 * T2_NEPI);
+        }
+        const int NT0 = T0.NT, nflush = (T0.nkb + F - 1) / F;
+        for (int f = 0; f < nflush; ++f, ++acc_it) {
+          const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+          mbar_wait(&sh.acc_full[buf], aph);
           fence_after_sync();
-          float v[16];
-          const float* c = coef + kb * KBLK + 16 * kh;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 c0 = t2_ld4s(c + 4 * i), c1 = t2_ld4s(c + Kc + 4 * i), c2 = t2_ld4s(c + 2 * Kc + 4 * i);
-            v[4 * i] = fmaf(c0.x, x[i].x, fmaf(c1.x, w[i].x, c2.x));
-            v[4 * i + 1] = fmaf(c0.y, x[i].y, fmaf(c1.y, w[i].y, c2.y));
-            v[4 * i + 2] = fmaf(c0.z, x[i].z, fmaf(c1.z, w[i].z, c2.z));
-            v[4 * i + 3] = fmaf(c0.w, x[i].w, fmaf(c1.w, w[i].w, c2.w));
-          }
-          t2_store_split16(ta + (uint32_t)r.s * 64u, v);
-          if (kb + 1 < T.nkb) load(kb + 1);
-          tmem_st_wait();
+          t2_drain_add(tmem + buf * T2_ACC_COLS, q, ch, NT0, acc);
           fence_before_sync();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&sh.full_a[r.s]);
+          if (lane == 0) mbar_arrive(&sh.acc_empty[buf]);
         }
       }
-    }
-  } else {
-    // ===== epilogue warps =====
-    const int e = warp - T2_NSTAGER, q = warp & 3, ch = e >> 2, etid = tid - 32 * T2_NSTAGER;
-    const int arow = 32 * q + lane;                  // accumulator row this thread drains
-    const int rsub = lane >> 4, c4 = (lane & 15) * 4;   // coalesced pass: 16 lanes per row, 2 rows per warp step
-    float* ot = reinterpret_cast<float*>(smem + p.off_ot);
-    double* red = reinterpret_cast<double*>(smem + p.off_red);
-    float* ccs = reinterpret_cast<float*>(smem + p.off_ccs);
-    uint32_t acc_it = 0;
-    for (int t = t_begin; t < t_end; ++t) {
-      const T2Tile T = t2_decode<MODE>(p, t);
+      int t_again = t;
+      asm volatile("" : "+r"(t_again));              // keeps the decode below from being carried through the drain loop
+      const T2Tile T = t2_decode<MODE>(p, t_again, crank);
       const FcGroup& G = p.g[T.g];
       const ActDev& D = G.A;                          // dgrad: the destination
       const int Nfull = (MODE == T2_FWD) ? G.Y.n : D.n;
       const int Nend = min(Nfull, T.n0 + T.NT);
-      bool plainD = true, has_norm = false;
-      if (MODE == T2_DGRAD) {
-        has_norm = D.norm.mode != SWR_NORM_NONE;
-        plainD = !has_norm && D.act == SWR_ACT_NONE;
-        // coefficients of the destination's own norm / activation: [4][NT] mu, s, b, r
-        named_bar(T2_BAR_EPI, 32 * T2_NEPI);
-        for (int c = etid; c < T.NT; c += 32 * T2_NEPI) {
-          ColCoef cc = {0.f, 1.f, 0.f, 1.f};
-          if (!plainD && T.n0 + c < Nend) cc = col_coef(D.norm, T.n0 + c, p.inv_count);
-          ccs[c] = cc.mu; ccs[T.NT + c] = cc.s; ccs[2 * T.NT + c] = cc.b; ccs[3 * T.NT + c] = cc.r;
-        }
-        named_bar(T2_BAR_EPI, 32 * T2_NEPI);
-      }
-      float acc[64];
-#pragma unroll
-      for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-      const int nflush = (T.nkb + F - 1) / F;
-      for (int f = 0; f < nflush; ++f, ++acc_it) {
-        const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
-        mbar_wait(&sh.acc_full[buf], aph);
-        fence_after_sync();
-        t2_drain_add(tmem + buf * T2_ACC_COLS, q, ch, T.NT, acc);
-        fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sh.acc_empty[buf]);
-      }
-      // ---- final epilogue, 64 accumulator columns per pass ----
-      for (int pass = 0; pass < 2; ++pass) {
-        const int pc0 = 64 * pass;
-        if (pc0 >= T.NT) break;
-        const int pc = min(64, T.NT - pc0);
+      const bool has_norm = (MODE == T2_DGRAD) && D.norm.mode != SWR_NORM_NONE;
+      const bool plainD = (MODE != T2_DGRAD) || (!has_norm && D.act == SWR_ACT_NONE);
+      const int gtid = (tid - 32 * T2_NSTAGER) & 127;
+      const int arow = 32 * q + lane;                  // accumulator row this thread drains
+      const int rsub = lane >> 3, c4 = (lane & 7) * 4;  // coalesced pass: 8 lanes per row, 4 rows per warp step
+      const int bar_g = T2_BAR_EGRP + ch;
+      float* ot = reinterpret_cast<float*>(smem + p.off_ot) + ch * T2_OT_GROUP;
+      const uint32_t ot_s = smem_s + (uint32_t)p.off_ot + (uint32_t)(ch * T2_OT_GROUP) * 4u;
+      float* red = reinterpret_cast<float*>(smem + p.off_red) + ch * T2_RED_GROUP;     // [2][4 warps][32]
+      float* ccs = reinterpret_cast<float*>(smem + p.off_ccs);
+      // ---- final epilogue of this group's columns, 32 per pass ----
+      // Column statistics stay in fp32 until one thread per column widens them (fp64 throughput is a small fraction
+      // of fp32's): forward moments are sums of deviations from the tile's first row, a centre every thread can read.
+      const int cnt_rows = min(T2_BM, M - T.m0);
+      const int row_base = 32 * q + rsub;            // this lane's rows: row_base + 4 i
+      const int rows_here = min((max(cnt_rows - row_base, 0) + 3) >> 2, 8);
+#pragma unroll 1
+      for (int sp = 0; sp < 2; ++sp) {
+        const int pc0 = 64 * ch + 32 * sp;
+        if (pc0 >= T.NT) break;                      // uniform over the group
+        const int pc = min(32, T.NT - pc0);
         const int nvalid = min(max(Nend - (T.n0 + pc0), 0), pc);
-        named_bar(T2_BAR_EPI, 32 * T2_NEPI);          // everybody is done with the previous contents of ot / red
-        if (ch == pass) t2_acc_to_smem(ot, arow, pc, acc);
-        named_bar(T2_BAR_EPI, 32 * T2_NEPI);
+        if (e == 0 && lane == 0) { T2_STAMP(3, ev3); ++ev3; }
+        named_bar(bar_g, 128);                       // the group is done with the previous contents of ot / red
+        if (e == 0 && lane == 0) { T2_STAMP(3, ev3); ++ev3; }
+        t2_acc_to_smem(ot_s, arow, sp, pc, acc);
+        if (e == 0 && lane == 0) { T2_STAMP(3, ev3); ++ev3; }
+        named_bar(bar_g, 128);
+        if (e == 0 && lane == 0) { T2_STAMP(3, ev3); ++ev3; }
         const int nv = nvalid - c4;                  // valid components of this lane's column quad (<= 0: none)
         const int n = T.n0 + pc0 + c4;               // first output column of the quad
-        double s1d[4] = {0.0, 0.0, 0.0, 0.0}, s2d[4] = {0.0, 0.0, 0.0, 0.0};
+        const uint32_t my_ot = ot_s + (uint32_t)(row_base * T2_OT_LD + c4) * 4u;   // + i * 4 rows
+        float4 s1 = t2_zero4(), s2 = t2_zero4();
         if (MODE == T2_FWD) {
           float* Y = const_cast<float*>(G.Y.raw);
           const bool vec = (nv >= 4) && (G.Y.ld % 4 == 0) && is_al16(Y) && (n % 4 == 0);
           if (nv > 0) {
-            float bias[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) bias[j] = (j < nv) ? ld_opt(G.bias, n + j, 0.f) + ld_opt(G.bias2, n + j, 0.f) : 0.f;
-            // moments of this lane's 8 rows: fp32 sums centred on the first value, widened to fp64 once
-            float t1[4] = {0.f, 0.f, 0.f, 0.f}, t2[4] = {0.f, 0.f, 0.f, 0.f}, y0[4] = {0.f, 0.f, 0.f, 0.f};
-            int cnt = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = 16 * e + 2 * i + rsub, m = T.m0 + rr;
-              if (m < M) {
-                const float4 a4 = t2_ld4s(ot + (size_t)rr * T2_OT_LD + c4);
-                float y[4] = {a4.x + bias[0], a4.y + bias[1], a4.z + bias[2], a4.w + bias[3]};
-                if (G.e_act != SWR_ACT_NONE) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) y[j] = act_fwd(y[j], G.e_act) * G.e_scale;
-                }
-                float* dst = Y + (int64_t)m * G.Y.ld + n;
-                if (vec) *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
-                else {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) if (j < nv) dst[j] = y[j];
-                }
-                if (cnt == 0) { y0[0] = y[0]; y0[1] = y[1]; y0[2] = y[2]; y0[3] = y[3]; }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { const float dlt = y[j] - y0[j]; t1[j] += dlt; t2[j] = fmaf(dlt, dlt, t2[j]); }
-                ++cnt;
+            float4 bias;
+            bias.x = ld_opt(G.bias, n, 0.f) + ld_opt(G.bias2, n, 0.f);
+            bias.y = nv > 1 ? ld_opt(G.bias, n + 1, 0.f) + ld_opt(G.bias2, n + 1, 0.f) : 0.f;
+            bias.z = nv > 2 ? ld_opt(G.bias, n + 2, 0.f) + ld_opt(G.bias2, n + 2, 0.f) : 0.f;
+            bias.w = nv > 3 ? ld_opt(G.bias, n + 3, 0.f) + ld_opt(G.bias2, n + 3, 0.f) : 0.f;
+            float* dst = Y + (int64_t)(T.m0 + row_base) * G.Y.ld + n;
+            const int64_t dstep = 4 * (int64_t)G.Y.ld;
+            const float4 r0 = lds128(ot_s + (uint32_t)c4 * 4u);      // row 0 of the tile: always a valid batch row
+            if (G.e_act == SWR_ACT_NONE && vec) {   // the common case, branch-free per row
+              const float4 y0 = make_float4(r0.x + bias.x, r0.y + bias.y, r0.z + bias.z, r0.w + bias.w);
+              if (y0.x == 1234.5f) s1.x = 1.f;
+              if (e == 0 && lane == 0) { T2_STAMP(3, ev3); ++ev3; }
+#pragma unroll 2
+              for (int i = 0; i < rows_here; ++i) {
+                const float4 a = lds128(my_ot + (uint32_t)(4 * i * T2_OT_LD) * 4u);
+                const float4 y = make_float4(a.x + bias.x, a.y + bias.y, a.z + bias.z, a.w + bias.w);
+                *reinterpret_cast<float4*>(dst + i * dstep) = y;
+                const float4 d = make_float4(y.x - y0.x, y.y - y0.y, y.z - y0.z, y.w - y0.w);
+                s1.x += d.x; s1.y += d.y; s1.z += d.z; s1.w += d.w;
+                s2.x = fmaf(d.x, d.x, s2.x); s2.y = fmaf(d.y, d.y, s2.y); s2.z = fmaf(d.z, d.z, s2.z); s2.w = fmaf(d.w, d.w, s2.w);
               }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const double dy0 = (double)y0[j], dt1 = (double)t1[j];
-              s1d[j] = (double)cnt * dy0 + dt1;
-              s2d[j] = (double)cnt * dy0 * dy0 + 2.0 * dy0 * dt1 + (double)t2[j];
+            } else {
+              const float4 y0 = make_float4(t2_epi_val(r0.x, bias.x, G.e_act, G.e_scale), t2_epi_val(r0.y, bias.y, G.e_act, G.e_scale),
+                                            t2_epi_val(r0.z, bias.z, G.e_act, G.e_scale), t2_epi_val(r0.w, bias.w, G.e_act, G.e_scale));
+#pragma unroll 1
+              for (int i = 0; i < rows_here; ++i) {
+                const float4 a = lds128(my_ot + (uint32_t)(4 * i * T2_OT_LD) * 4u);
+                const float4 y = make_float4(t2_epi_val(a.x, bias.x, G.e_act, G.e_scale), t2_epi_val(a.y, bias.y, G.e_act, G.e_scale),
+                                             t2_epi_val(a.z, bias.z, G.e_act, G.e_scale), t2_epi_val(a.w, bias.w, G.e_act, G.e_scale));
+                float* dp = dst + i * dstep;
+                if (vec) *reinterpret_cast<float4*>(dp) = y;
+                else { dp[0] = y.x; if (nv > 1) dp[1] = y.y; if (nv > 2) dp[2] = y.z; if (nv > 3) dp[3] = y.w; }
+                const float4 d = make_float4(y.x - y0.x, y.y - y0.y, y.z - y0.z, y.w - y0.w);
+                s1.x += d.x; s1.y += d.y; s1.z += d.z; s1.w += d.w;
+                s2.x = fmaf(d.x, d.x, s2.x); s2.y = fmaf(d.y, d.y, s2.y); s2.z = fmaf(d.z, d.z, s2.z); s2.w = fmaf(d.w, d.w, s2.w);
+              }
             }
           }
         } else {
@@ -487,29 +614,53 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
           const bool vec = (nv >= 4) && (D.ld % 4 == 0) && is_al16(D.dz) && is_al16(D.raw) && (n % 4 == 0);
           if (nv > 0) {
             const int cc0 = pc0 + c4;
-            const float4 mu4 = t2_ld4s(ccs + cc0), sc4 = t2_ld4s(ccs + T.NT + cc0), bb4 = t2_ld4s(ccs + 2 * T.NT + cc0), rr4 = t2_ld4s(ccs + 3 * T.NT + cc0);
-            const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w};
-            const float bb[4] = {bb4.x, bb4.y, bb4.z, bb4.w}, rr_[4] = {rr4.x, rr4.y, rr4.z, rr4.w};
-            float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = 16 * e + 2 * i + rsub, m = T.m0 + rr;
-              if (m < M) {
-                const float4 a4 = t2_ld4s(ot + (size_t)rr * T2_OT_LD + c4);
-                float dz[4] = {a4.x, a4.y, a4.z, a4.w};
-                const int64_t o = (int64_t)m * D.ld + n;
-                if (!plainD) {
-                  float raw[4];
-                  if (vec) { const float4 r4 = *reinterpret_cast<const float4*>(D.raw + o); raw[0] = r4.x; raw[1] = r4.y; raw[2] = r4.z; raw[3] = r4.w; }
-                  else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) raw[j] = (j < nv) ? D.raw[o + j] : 0.f;
+            const int64_t o0 = (int64_t)(T.m0 + row_base) * D.ld + n, ostep = 4 * (int64_t)D.ld;
+            if (vec && !atomic_dst) {              // the common case
+              const float4 mu = t2_ld4s(ccs + cc0), sc = t2_ld4s(ccs + T.NT + cc0), bb = t2_ld4s(ccs + 2 * T.NT + cc0), rr4 = t2_ld4s(ccs + 3 * T.NT + cc0);
+              const float slope = t2_slope(D.act);
+              const bool sigD = D.act == SWR_ACT_SIGMOID;
+#pragma unroll 2
+              for (int i = 0; i < rows_here; ++i) {
+                {
+                  float4 dz = lds128(my_ot + (uint32_t)(4 * i * T2_OT_LD) * 4u);
+                  float* dst = D.dz + o0 + i * ostep;
+                  if (!plainD) {
+                    const float4 raw = *reinterpret_cast<const float4*>(D.raw + o0 + i * ostep);
+                    const float4 xc = make_float4(raw.x - mu.x, raw.y - mu.y, raw.z - mu.z, raw.w - mu.w);
+                    const float4 z = make_float4(fmaf(xc.x, sc.x, bb.x), fmaf(xc.y, sc.y, bb.y), fmaf(xc.z, sc.z, bb.z), fmaf(xc.w, sc.w, bb.w));
+                    if (sigD) {
+                      dz.x *= act_grad(z.x, SWR_ACT_SIGMOID); dz.y *= act_grad(z.y, SWR_ACT_SIGMOID);
+                      dz.z *= act_grad(z.z, SWR_ACT_SIGMOID); dz.w *= act_grad(z.w, SWR_ACT_SIGMOID);
+                    } else {       // d max(z, slope z) / dz
+                      dz.x *= z.x > 0.f ? 1.f : slope; dz.y *= z.y > 0.f ? 1.f : slope;
+                      dz.z *= z.z > 0.f ? 1.f : slope; dz.w *= z.w > 0.f ? 1.f : slope;
+                    }
+                    s1.x += dz.x; s1.y += dz.y; s1.z += dz.z; s1.w += dz.w;
+                    s2.x = fmaf(dz.x, xc.x * rr4.x, s2.x); s2.y = fmaf(dz.y, xc.y * rr4.y, s2.y);
+                    s2.z = fmaf(dz.z, xc.z * rr4.z, s2.z); s2.w = fmaf(dz.w, xc.w * rr4.w, s2.w);
                   }
+                  if (accumulate) { const float4 old = *reinterpret_cast<const float4*>(dst); dz.x += old.x; dz.y += old.y; dz.z += old.z; dz.w += old.w; }
+                  *reinterpret_cast<float4*>(dst) = dz;
+                }
+              }
+            } else {
+              const float mu[4] = {ccs[cc0], ccs[cc0 + 1], ccs[cc0 + 2], ccs[cc0 + 3]};
+              const float sc[4] = {ccs[T.NT + cc0], ccs[T.NT + cc0 + 1], ccs[T.NT + cc0 + 2], ccs[T.NT + cc0 + 3]};
+              const float bb[4] = {ccs[2 * T.NT + cc0], ccs[2 * T.NT + cc0 + 1], ccs[2 * T.NT + cc0 + 2], ccs[2 * T.NT + cc0 + 3]};
+              const float rr_[4] = {ccs[3 * T.NT + cc0], ccs[3 * T.NT + cc0 + 1], ccs[3 * T.NT + cc0 + 2], ccs[3 * T.NT + cc0 + 3]};
+              float t1[4] = {0.f, 0.f, 0.f, 0.f}, t2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+              for (int i = 0; i < rows_here; ++i) {
+                const float4 a4 = lds128(my_ot + (uint32_t)(4 * i * T2_OT_LD) * 4u);
+                float dz[4] = {a4.x, a4.y, a4.z, a4.w};
+                const int64_t o = o0 + i * ostep;
+                if (!plainD) {
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
-                    dz[j] *= act_grad(fmaf(raw[j] - mu[j], sc[j], bb[j]), D.act);
-                    s1[j] += dz[j];
-                    s2[j] = fmaf(dz[j], (raw[j] - mu[j]) * rr_[j], s2[j]);
+                    const float raw = (j < nv) ? D.raw[o + j] : 0.f;
+                    dz[j] *= act_grad(fmaf(raw - mu[j], sc[j], bb[j]), D.act);
+                    t1[j] += dz[j];
+                    t2[j] = fmaf(dz[j], (raw - mu[j]) * rr_[j], t2[j]);
                   }
                 }
                 float* dst = D.dz + o;
@@ -519,47 +670,65 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
 #pragma unroll
                     for (int j = 0; j < 4; ++j) if (j < nv) atomicAdd(dst + j, dz[j]);
                   }
-                } else if (vec) {
-                  float4 o4 = make_float4(dz[0], dz[1], dz[2], dz[3]);
-                  if (accumulate) { const float4 old = *reinterpret_cast<const float4*>(dst); o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w; }
-                  *reinterpret_cast<float4*>(dst) = o4;
                 } else {
 #pragma unroll
                   for (int j = 0; j < 4; ++j) if (j < nv) dst[j] = accumulate ? dst[j] + dz[j] : dz[j];
                 }
               }
+              s1 = make_float4(t1[0], t1[1], t1[2], t1[3]); s2 = make_float4(t2[0], t2[1], t2[2], t2[3]);
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { s1d[j] = (double)s1[j]; s2d[j] = (double)s2[j]; }
           }
         }
+        if (e == 0 && lane == 0) { T2_STAMP(3, ev3); ++ev3; }
         const bool want_stats = (MODE == T2_FWD) ? (G.stats_out != nullptr) : (has_norm && D.dstats != nullptr);
-        if (want_stats) {           // uniform over the epilogue warps
+        if (want_stats) {           // uniform over the group
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            s1d[j] += __shfl_xor_sync(0xffffffffu, s1d[j], 16);
-            s2d[j] += __shfl_xor_sync(0xffffffffu, s2d[j], 16);
+          for (int o = 8; o <= 16; o <<= 1) {          // the four row sub-groups of the warp
+            s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
+            s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
+            s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
+            s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
           }
           if (rsub == 0 && nv > 0) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { red[(0 * T2_NEPI + e) * 64 + c4 + j] = s1d[j]; red[(1 * T2_NEPI + e) * 64 + c4 + j] = s2d[j]; }
+            *reinterpret_cast<float4*>(red + (0 * 4 + q) * 32 + c4) = s1;
+            *reinterpret_cast<float4*>(red + (1 * 4 + q) * 32 + c4) = s2;
           }
-          named_bar(T2_BAR_EPI, 32 * T2_NEPI);
-          t2_col_atomics(red, (MODE == T2_FWD) ? G.stats_out : D.dstats, T.n0 + pc0, nvalid, etid);
-        }
+          if (e == 0 && lane == 0) { T2_STAMP(3, ev3); ++ev3; }
+          named_bar(bar_g, 128);
+          if (e == 0 && lane == 0) { T2_STAMP(3, ev3); ++ev3; }
+          if (gtid < nvalid && cnt_rows > 0) {      // one thread per column: fp32 sum over the group's warps, widened once
+            const float S1 = red[gtid] + red[32 + gtid] + red[64 + gtid] + red[96 + gtid];
+            const float S2 = red[128 + gtid] + red[160 + gtid] + red[192 + gtid] + red[224 + gtid];
+            const int col = T.n0 + pc0 + gtid;
+            if (MODE == T2_FWD) {
+              const float bias = ld_opt(G.bias, col, 0.f) + ld_opt(G.bias2, col, 0.f);
+              const double y0 = (double)t2_epi_val(ot[gtid], bias, G.e_act, G.e_scale), c = (double)cnt_rows, d1 = (double)S1;
+              atomicAdd(G.stats_out + 2 * col, c * y0 + d1);
+              atomicAdd(G.stats_out + 2 * col + 1, c * y0 * y0 + 2.0 * y0 * d1 + (double)S2);
+            } else {
+              atomicAdd(D.dstats + 2 * col, (double)S1);
+              atomicAdd(D.dstats + 2 * col + 1, (double)S2);
+            }
+          }
+          if (e == 0 && lane == 0) { T2_STAMP(3, ev3); ++ev3; }
+          }
       }
     }
   }
+  if (tid == 32 * T2_NSTAGER) T2_STAMP(3, 127);
+  if (tid == 0) T2_STAMP(2, 127);
   fence_before_sync();
   __syncthreads();
+  if (C > 1) cluster_sync_all();           // no CTA leaves while a peer may still signal its barriers
   if (warp == T2_W_MMA) { __syncwarp(); tmem_dealloc(tmem, T2_TMEM_COLS); }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // weight / bias gradient: dWeff[n, j] = sum_b dY[b, n] * act(norm(A))[b, j],  db[n] = sum_b dY[b, n]
 // accumulator rows = output features n, columns = input features j, contraction = the batch rows of one split.
-// Both operands are computed: dY^T goes registers -> TMEM (lane = output feature, coalesced 128-byte reads over
-// 32 features per batch row), the activations go to shared memory in the MN-major swizzled layout.  No TMA here.
+// TMA brings three raw tiles per k-block (32 batch rows): dz [32][128 n], raw output [32][128 n] (BatchNorm layers),
+// input activation [32][NT j], unswizzled.  The stagers form dY^T in registers (lane = output feature) -> TMEM, and
+// act(norm(A)) -> hi / lo MN-major swizzled tiles in shared memory (the MMA's column operand).
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ T2Tile t2_decode_wgrad(const Tc2Params& p, int t) {
   T2Tile T{};
@@ -584,44 +753,70 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_wgrad_kernel(const __gri
   uint8_t* smem = t2_align1024(smem_raw);
   const uint32_t smem_s = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int S = p.stages, F = p.flush;
+  const int SB = p.sb, SR = p.sr, F = p.flush;
   int t_begin, t_end;
-  t2_range(p.n_tiles, t_begin, t_end);
-  t2_setup(sh, S, tid, warp);
+  t2_range(p.n_tiles, 1, t_begin, t_end);
+  t2_setup(sh, tid, warp, T2_NSTAGER, 1);
   const uint32_t tmem = sh.tmem_base;
-
-  if (warp == T2_W_MMA) {
-    if (lane == 0) {
-      T2Ring r; r.init();
-      uint32_t acc_it = 0;
-      for (int t = t_begin; t < t_end; ++t) {
-        const T2Tile T = t2_decode_wgrad(p, t);
-        const uint32_t b_bytes = (uint32_t)T.NT * 128u, stage_bytes = (uint32_t)p.stage_bytes;
-        const uint32_t idesc = make_idesc_tf32(T2_BM, T.NT, false, true);
-        int fpos = 0;
-        for (int kb = 0; kb < T.nkb; ++kb, r.next(S)) {
-          const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
-          if (fpos == 0) { mbar_wait(&sh.acc_empty[buf], aph ^ 1u); fence_after_sync(); }
-          mbar_wait(&sh.full_a[r.s], r.ph);
-          fence_after_sync();
-          t2_issue(tmem + buf * T2_ACC_COLS, tmem + T2_A_COL0 + (uint32_t)r.s * 64u, smem_s + (uint32_t)r.s * stage_bytes, b_bytes,
-                   true, idesc, fpos == 0);
-          mma_commit(&sh.empty[r.s]);
-          if (++fpos == F || kb == T.nkb - 1) { mma_commit(&sh.acc_full[buf]); ++acc_it; fpos = 0; }
+  if (warp == T2_W_TMA) {
+    T2Ring rr; rr.init();
+    for (int t = t_begin; t < t_end; ++t) {
+      const T2Tile T = t2_decode_wgrad(p, t);
+      const FcGroup& G = p.g[T.g];
+      const bool two = G.Y.norm.mode == SWR_NORM_BATCH;
+      const uint32_t bytes = (two ? 2u : 1u) * T2_RAW_BYTES + 32u * (uint32_t)T.NT * 4u;
+      for (int kb = 0; kb < T.nkb; ++kb, rr.next(SR)) {
+        mbar_wait(&sh.empty_r[rr.s], rr.ph ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(&sh.full_r[rr.s], bytes);
+          const uint32_t rdst = smem_s + (uint32_t)(p.off_r + rr.s * p.stage_r);
+          const int b0 = T.b_begin + kb * KBLK;
+          tma_load_2d(rdst, &p.tm0[T.g], T.m0, b0, &sh.full_r[rr.s]);
+          if (two) tma_load_2d(rdst + T2_RAW_BYTES, &p.tm1[T.g], T.m0, b0, &sh.full_r[rr.s]);
+          tma_load_2d(rdst + 2 * T2_RAW_BYTES, &p.tm2[T.g], T.n0, b0, &sh.full_r[rr.s]);
         }
+        __syncwarp();
+      }
+    }
+  } else if (warp == T2_W_MMA) {
+    T2Ring ra; ra.init();
+    uint32_t acc_it = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      const T2Tile T = t2_decode_wgrad(p, t);
+      const uint32_t b_bytes = (uint32_t)T.NT * 128u;
+      const uint32_t idesc = make_idesc_tf32(T2_BM, T.NT, false, true);
+      int fpos = 0;
+      for (int kb = 0; kb < T.nkb; ++kb, ra.next(SB)) {
+        const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+        if (fpos == 0) mbar_wait(&sh.acc_empty[buf], aph ^ 1u);
+        mbar_wait(&sh.full_a[ra.s], ra.ph);
+        fence_after_sync();
+        const bool last = (fpos + 1 == F) || (kb == T.nkb - 1);
+        if (elect_one()) {
+          t2_issue(tmem + buf * T2_ACC_COLS, tmem + T2_A_COL0 + (uint32_t)ra.s * 64u, smem_s + (uint32_t)(ra.s * p.stage_b), b_bytes,
+                   true, idesc, fpos == 0);
+          mma_commit(&sh.empty_a[ra.s]);
+          if (last) mma_commit(&sh.acc_full[buf]);
+        }
+        __syncwarp();
+        if (last) { ++acc_it; fpos = 0; } else ++fpos;
       }
     }
   } else if (warp < T2_NSTAGER) {
     const int q = warp & 3, kh = warp >> 2, stid = tid;
+    const int nl = 32 * q + lane;                    // output feature inside the tile = TMEM lane
     const uint32_t ta = tmem + T2_A_COL0 + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * kh);
     float* coef = reinterpret_cast<float*>(smem + p.off_coef);   // [3][NT]: mu, s, b of the input columns of the tile
-    T2Ring r; r.init();
+    T2Ring rr, ra; rr.init(); ra.init();
     int cur_g = -1, cur_n0 = -1;
     for (int t = t_begin; t < t_end; ++t) {
       const T2Tile T = t2_decode_wgrad(p, t);
       if (T.nkb == 0) continue;
       const FcGroup& G = p.g[T.g];
-      const int N = G.Y.n, K = G.A.n, NT = T.NT, nq = NT >> 2, nit = NT >> 5;   // float4 per thread and k-block of the column operand
+      const int N = G.Y.n, K = G.A.n, NT = T.NT;
+      const int lg = (NT == 128) ? 5 : (NT == 64 ? 4 : 3);       // log2(NT / 4): float4 quads per row of the column operand
+      const int nit = NT >> 5;                                    // float4 per thread and k-block
+      const int qd = stid & ((1 << lg) - 1), c0 = stid >> lg, cstep = (32 * T2_NSTAGER) >> lg;
       const bool plainA = (G.A.norm.mode == SWR_NORM_NONE && G.A.act == SWR_ACT_NONE);
       if (cur_g != T.g || cur_n0 != T.n0) {
         named_bar(T2_BAR_STAGE, 32 * T2_NSTAGER);
@@ -633,84 +828,65 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_wgrad_kernel(const __gri
         named_bar(T2_BAR_STAGE, 32 * T2_NSTAGER);
         cur_g = T.g; cur_n0 = T.n0;
       }
-      const int n = T.m0 + 32 * q + lane;             // the output feature this thread stages
+      const int n = T.m0 + nl;
       const bool n_ok = n < N;
       DyCoef dc = {0.f, 0.f, 0.f};
       if (n_ok) dc = dy_coef(G.Y, n, p.inv_count);
-      const bool need_raw = (G.Y.norm.mode == SWR_NORM_BATCH);
+      const bool two = (G.Y.norm.mode == SWR_NORM_BATCH);
       const float slope = t2_slope(G.A.act);
       const bool sig = G.A.act == SWR_ACT_SIGMOID;
       const int rows = T.b_end - T.b_begin;
-      const float* dzp = G.Y.dz + (int64_t)T.b_begin * G.Y.ld + (n_ok ? n : 0);
-      const float* rwp = G.Y.raw + (int64_t)T.b_begin * G.Y.ld + (n_ok ? n : 0);
-      const float* ap = G.A.raw + (int64_t)T.b_begin * G.A.ld + T.n0;
-      const bool vecA = is_al16(G.A.raw) && (G.A.ld % 4 == 0) && (T.n0 % 4 == 0);
+      // this thread's input-column coefficients do not change over the k-blocks of a tile
+      const float4 cmu = t2_ld4s(coef + 4 * qd), csc = t2_ld4s(coef + NT + 4 * qd), cbb = t2_ld4s(coef + 2 * NT + 4 * qd);
+      const uint32_t b_bytes = (uint32_t)NT * 128u;
       float rowsum = 0.f;
-      float xa[16], xr[16];
-      float4 xb[4];
-      auto load = [&](int kb) {
-        const int b0 = kb * KBLK + 16 * kh;
+      for (int kb = 0; kb < T.nkb; ++kb, rr.next(SR), ra.next(SB)) {
+        mbar_wait(&sh.full_r[rr.s], rr.ph);
+        const float* rt = reinterpret_cast<const float*>(smem + p.off_r + rr.s * p.stage_r);
+        // ---- dY^T: 16 batch rows of output feature n ----
+        float v[16];
+        const int left = n_ok ? rows - (kb * KBLK + 16 * kh) : 0;   // c2 != 0: contraction padding must stay exactly zero
+        const float* dzs = rt + (16 * kh) * T2_BM + nl;
+        if (two) {
+          const float* rws = dzs + T2_RAW_BYTES / 4;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const bool ok = n_ok && (b0 + i < rows);
-          xa[i] = ok ? __ldg(dzp + (int64_t)(b0 + i) * G.Y.ld) : 0.f;
-          xr[i] = (ok && need_raw) ? __ldg(rwp + (int64_t)(b0 + i) * G.Y.ld) : 0.f;
+          for (int i = 0; i < 16; ++i) v[i] = (i < left) ? fmaf(dc.c0, dzs[i * T2_BM], fmaf(dc.c1, rws[i * T2_BM], dc.c2)) : 0.f;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = (i < left) ? fmaf(dc.c0, dzs[i * T2_BM], dc.c2) : 0.f;
         }
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          if (it < nit) {
-            const int v = it * (32 * T2_NSTAGER) + stid, c = v / nq, qd = v - c * nq;
-            const int b = min(kb * KBLK + c, rows - 1);       // rows past the split meet an exactly-zero dY column
-            const int jv = K - (T.n0 + 4 * qd);
-            const float* src = ap + (int64_t)b * G.A.ld + 4 * qd;
-            if (vecA) xb[it] = t2_ld4_mask(src, jv);
-            else {
-              xb[it] = t2_zero4();
-              if (jv > 0) xb[it].x = __ldg(src);
-              if (jv > 1) xb[it].y = __ldg(src + 1);
-              if (jv > 2) xb[it].z = __ldg(src + 2);
-              if (jv > 3) xb[it].w = __ldg(src + 3);
-            }
-          }
-        }
-      };
-      load(0);
-      const uint32_t b_bytes = (uint32_t)NT * 128u, stage_bytes = (uint32_t)p.stage_bytes;
-      for (int kb = 0; kb < T.nkb; ++kb, r.next(S)) {
-        mbar_wait(&sh.empty[r.s], r.ph ^ 1u);
+        for (int i = 0; i < 16; ++i) rowsum += v[i];
+        // ---- act(norm(A)): float4 (batch row c, feature quad qd) ----
+        const float* as = rt + 2 * (T2_RAW_BYTES / 4);
+        float4 xb[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it)
+          if (it < nit) xb[it] = t2_ld4s(as + (c0 + it * cstep) * NT + 4 * qd);
+        mbar_wait(&sh.empty_a[ra.s], ra.ph ^ 1u);
         fence_after_sync();
-        {
-          float v[16];
-          const int b0 = kb * KBLK + 16 * kh;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const bool ok = n_ok && (b0 + i < rows);          // c2 != 0: contraction padding must stay exactly zero
-            v[i] = ok ? fmaf(dc.c0, xa[i], fmaf(dc.c1, xr[i], dc.c2)) : 0.f;
-            rowsum += v[i];
-          }
-          t2_store_split16(ta + (uint32_t)r.s * 64u, v);
-        }
-        const uint32_t bh = smem_s + (uint32_t)r.s * stage_bytes, bl = bh + b_bytes;
+        t2_store_split16(ta + (uint32_t)ra.s * 64u, v);
+        const uint32_t bh = smem_s + (uint32_t)(ra.s * p.stage_b), bl = bh + b_bytes;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           if (it < nit) {
-            const int v = it * (32 * T2_NSTAGER) + stid, c = v / nq, qd = v - c * nq;
             float4 x = xb[it];
             if (!plainA) {
-              const float* cf = coef + 4 * qd;
-              const float4 mu = t2_ld4s(cf), sc = t2_ld4s(cf + NT), bb = t2_ld4s(cf + 2 * NT);
-              x.x = t2_act(fmaf(x.x - mu.x, sc.x, bb.x), slope, sig); x.y = t2_act(fmaf(x.y - mu.y, sc.y, bb.y), slope, sig);
-              x.z = t2_act(fmaf(x.z - mu.z, sc.z, bb.z), slope, sig); x.w = t2_act(fmaf(x.w - mu.w, sc.w, bb.w), slope, sig);
+              x.x = fmaf(x.x - cmu.x, csc.x, cbb.x); x.y = fmaf(x.y - cmu.y, csc.y, cbb.y);
+              x.z = fmaf(x.z - cmu.z, csc.z, cbb.z); x.w = fmaf(x.w - cmu.w, csc.w, cbb.w);
+              if (sig) { x.x = 1.f / (1.f + expf(-x.x)); x.y = 1.f / (1.f + expf(-x.y)); x.z = 1.f / (1.f + expf(-x.z)); x.w = 1.f / (1.f + expf(-x.w)); }
+              else { x.x = fmaxf(x.x, slope * x.x); x.y = fmaxf(x.y, slope * x.y); x.z = fmaxf(x.z, slope * x.z); x.w = fmaxf(x.w, slope * x.w); }
             }
-            store_split(bh, bl, mnmajor_off(qd, c), x);
+            store_split(bh, bl, mnmajor_off(qd, c0 + it * cstep), x);
           }
         }
-        if (kb + 1 < T.nkb) load(kb + 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.empty_r[rr.s]);
         fence_proxy_async();      // shared-memory stores -> visible to the MMA unit
         tmem_st_wait();
         fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sh.full_a[r.s]);
+        if (lane == 0) mbar_arrive(&sh.full_a[ra.s]);
       }
       if (T.n0 == 0 && n_ok) {    // bias gradient: the j-tile 0 CTAs carry it (two threads per output feature)
         if (G.dbias) atomicAdd(G.dbias + n, rowsum);
@@ -718,10 +894,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_wgrad_kernel(const __gri
       }
     }
   } else if (warp < T2_NSTAGER + T2_NEPI) {
+    // two independent epilogue groups, see fc_tc2_kernel
     const int e = warp - T2_NSTAGER, q = warp & 3, ch = e >> 2;
     const int arow = 32 * q + lane;
-    const int rsub = lane >> 4, c4 = (lane & 15) * 4;
-    float* ot = reinterpret_cast<float*>(smem + p.off_ot);
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+    const int bar_g = T2_BAR_EGRP + ch;
+    const float* ot = reinterpret_cast<const float*>(smem + p.off_ot) + ch * T2_OT_GROUP;
+    const uint32_t ot_s = smem_s + (uint32_t)p.off_ot + (uint32_t)(ch * T2_OT_GROUP) * 4u;
     uint32_t acc_it = 0;
     for (int t = t_begin; t < t_end; ++t) {
       const T2Tile T = t2_decode_wgrad(p, t);
@@ -743,42 +922,46 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_wgrad_kernel(const __gri
       }
       const bool kn = (G.w_layout == SWR_W_KN);
       const int mvalid = min(N - T.m0, T2_BM);
-      for (int pass = 0; pass < 2; ++pass) {
-        const int pc0 = 64 * pass;
+      const int row_base = 32 * q + rsub;
+      const int rows_here = min((max(mvalid - row_base, 0) + 3) >> 2, 8);
+      for (int sp = 0; sp < 2; ++sp) {
+        const int pc0 = 64 * ch + 32 * sp;
         if (pc0 >= T.NT) break;
-        const int pc = min(64, T.NT - pc0);
+        const int pc = min(32, T.NT - pc0);
         const int nvalid = min(max(K - (T.n0 + pc0), 0), pc);
-        named_bar(T2_BAR_EPI, 32 * T2_NEPI);          // everybody is done reading the previous contents of ot
-        if (ch == pass) t2_acc_to_smem(ot, arow, pc, acc);
-        named_bar(T2_BAR_EPI, 32 * T2_NEPI);
+        named_bar(bar_g, 128);
+        t2_acc_to_smem(ot_s, arow, sp, pc, acc);
+        named_bar(bar_g, 128);
         const int j = T.n0 + pc0 + c4, nv = nvalid - c4;
-        if (!kn) {                                    // dW[n, j]: 16 lanes cover 64 consecutive input features of one output feature
+        if (!kn) {                                    // dW[n, j]: 8 lanes cover 32 consecutive input features of one output feature
           const bool vec = !G.W2 && G.dW && (nv >= 4) && (G.ldw % 4 == 0) && is_al16(G.dW) && (j % 4 == 0);
           if (nv > 0) {
+            const uint32_t my_ot = ot_s + (uint32_t)(row_base * T2_OT_LD + c4) * 4u;
+            const int64_t o0 = (int64_t)(T.m0 + row_base) * G.ldw + j, ostep = 4 * (int64_t)G.ldw;
+            if (vec) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = 16 * e + 2 * i + rsub;
-              if (rr < mvalid) {
-                const float4 a4 = t2_ld4s(ot + (size_t)rr * T2_OT_LD + c4);
-                const int64_t o = (int64_t)(T.m0 + rr) * G.ldw + j;
-                if (vec) t2_red_add_v4(G.dW + o, a4);
-                else {
-                  const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+              for (int i = 0; i < 8; ++i)
+                if (i < rows_here) t2_red_add_v4(G.dW + o0 + i * ostep, lds128(my_ot + (uint32_t)(4 * i * T2_OT_LD) * 4u));
+            } else {
+#pragma unroll 1
+              for (int i = 0; i < rows_here; ++i) {
+                const float4 a4 = lds128(my_ot + (uint32_t)(4 * i * T2_OT_LD) * 4u);
+                const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+                const int64_t o = o0 + i * ostep;
 #pragma unroll
-                  for (int jj = 0; jj < 4; ++jj) {
-                    if (jj < nv) {
-                      if (G.W2) {
-                        if (G.dW) atomicAdd(G.dW + o + jj, a[jj] * __ldg(G.W2 + o + jj));
-                        if (G.dW2) atomicAdd(G.dW2 + o + jj, a[jj] * __ldg(G.W + o + jj));
-                      } else if (G.dW) atomicAdd(G.dW + o + jj, a[jj]);
-                    }
+                for (int jj = 0; jj < 4; ++jj) {
+                  if (jj < nv) {
+                    if (G.W2) {
+                      if (G.dW) atomicAdd(G.dW + o + jj, a[jj] * __ldg(G.W2 + o + jj));
+                      if (G.dW2) atomicAdd(G.dW2 + o + jj, a[jj] * __ldg(G.W + o + jj));
+                    } else if (G.dW) atomicAdd(G.dW + o + jj, a[jj]);
                   }
                 }
               }
             }
           }
         } else {                                      // dW[j, n]: lanes run over output features n
-          for (int col = e; col < nvalid; col += T2_NEPI) {
+          for (int col = q; col < nvalid; col += 4) {
             for (int rb = 0; rb < T2_BM; rb += 32) {
               const int rr = rb + lane;
               if (rr < mvalid) {
@@ -901,18 +1084,33 @@ static t2_encode_fn t2_encoder() {
   }();
   return fn;
 }
-// image [2][rows][pitch] fp32 -> 3-D map {pitch, rows, 2}, box {32, box_rows, 2}, 128-byte swizzle; rows outside the
-// image read as zeros
-static int t2_make_map(CUtensorMap* tm, const float* img, int rows, int pitch, int box_rows) {
+// weight image [2][rows][pitch] fp32 -> 3-D map {pitch, rows, 2}, box {32, box_rows, 2}, 128-byte swizzle; rows outside
+// the image read as zeros
+static int t2_make_map(CUtensorMap* tm, const float* img, int rows, int pitch, int box_rows, int box_planes = 2) {
   t2_encode_fn enc = t2_encoder();
   if (!enc) { set_error("fc_tc2: cuTensorMapEncodeTiled is not available"); return SWR_ERR_UNSUPPORTED; }
   const cuuint64_t gdim[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, 2};
   const cuuint64_t gstr[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)rows * pitch * 4};
-  const cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 2};
+  const cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
   const cuuint32_t est[3] = {1, 1, 1};
   const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(img), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("fc_tc2: cuTensorMapEncodeTiled failed (%d) rows=%d pitch=%d box=%d", (int)r, rows, pitch, box_rows); return SWR_ERR_CUDA; }
+  return SWR_OK;
+}
+// activation [rows][ld] fp32 with `cols` valid columns -> 2-D map {cols, rows}, box {box_cols, box_rows}; elements
+// outside [cols) x [rows) read as zeros.  swizzled: 128-byte swizzle (box_cols == 32), else plain row-major tiles.
+static int t2_make_act_map(CUtensorMap* tm, const float* base, int rows, int cols, int ld, int box_cols, int box_rows, bool swizzled) {
+  t2_encode_fn enc = t2_encoder();
+  if (!enc) { set_error("fc_tc2: cuTensorMapEncodeTiled is not available"); return SWR_ERR_UNSUPPORTED; }
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t est[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         swizzled ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("fc_tc2: cuTensorMapEncodeTiled (activation) failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld); return SWR_ERR_CUDA; }
   return SWR_OK;
 }
 
@@ -920,7 +1118,7 @@ static int t2_pick_nt(int n) { return n <= 16 ? 16 : (n <= 32 ? 32 : (n <= 64 ? 
 static int t2_flush_for(int nt) {
   static int forced = [] { const char* e = getenv("SWR_TC_FLUSH"); return e ? atoi(e) : 0; }();
   if (forced > 0) return forced;
-  return nt >= 128 ? 1 : 128 / nt;       // >= ~768 MMA cycles between accumulator switches; chain <= 8 k-blocks
+  return 256 / nt;                        // NT = 128: every 2 k-blocks (192 products per truncated chain), the time one drain takes
 }
 
 template <class K>
@@ -941,24 +1139,64 @@ static int t2_set_smem(K kernel, size_t bytes) {
   return SWR_OK;
 }
 
-// shared-memory plan: [stages][2][NT][128 B] | coef | ccs | ot | red
-static int t2_plan_smem(Tc2Params& p, int nt_max, size_t coef_bytes, size_t ccs_bytes, int nkb_max, size_t* smem_bytes) {
-  const size_t stage = 2 * (size_t)nt_max * 128;
+// shared-memory plan: ring B [sb][stage_b] | ring R [sr][stage_r] | coef | ccs | ot | red
+static int t2_plan_smem(Tc2Params& p, size_t stage_b, size_t stage_r, size_t coef_bytes, size_t ccs_bytes, size_t* smem_bytes) {
   const size_t fixed = ((coef_bytes + 15) & ~(size_t)15) + ((ccs_bytes + 15) & ~(size_t)15) + T2_OT_BYTES + T2_RED_BYTES;
-  const size_t budget = 224 * 1024 - 1024;
-  if (fixed + 2 * stage > budget) { set_error("fc_tc2: tables of %zu bytes do not fit beside the stages", fixed); return SWR_ERR_UNSUPPORTED; }
-  int s = (int)((budget - fixed) / stage);
-  if (s > T2_MAX_STAGES) s = T2_MAX_STAGES;
-  if (s > nkb_max && nkb_max >= 2) s = nkb_max;
-  if (s < 2) s = 2;
-  p.stages = s;
-  p.stage_bytes = (int)stage;
-  size_t off = (size_t)s * stage;
+  // Stay inside the 196 KB shared-memory carve-out: the next step (228 KB) leaves the SM without L1, and the few
+  // registers the epilogue spills (64 running sums per thread in a 96-register budget) then cost an L2 round trip each.
+  static const size_t budget = [] { const char* e = getenv("SWR_TC_SMEM_KB"); return (size_t)(e ? atoi(e) : 195) * 1024 - 1024; }();
+  static const int pref[][2] = {{4, 4}, {4, 3}, {3, 3}, {4, 2}, {3, 2}, {2, 3}, {2, 2}};
+  int sb = 0, sr = 0;
+  for (auto& c : pref)
+    if (fixed + c[0] * stage_b + c[1] * stage_r <= budget) { sb = c[0]; sr = c[1]; break; }
+  if (!sb) { set_error("fc_tc2: %zu bytes of tables do not fit beside the stage rings", fixed); return SWR_ERR_UNSUPPORTED; }
+  p.sb = sb; p.sr = sr; p.stage_b = (int)stage_b; p.stage_r = (int)stage_r;
+  size_t off = (size_t)sb * stage_b;
+  p.off_r = (int)off; off += (size_t)sr * stage_r;
   p.off_coef = (int)off; off += (coef_bytes + 15) & ~(size_t)15;
   p.off_ccs = (int)off; off += (ccs_bytes + 15) & ~(size_t)15;
   p.off_ot = (int)off; off += T2_OT_BYTES;
   p.off_red = (int)off; off += T2_RED_BYTES;
   *smem_bytes = off + 1024;
+  return SWR_OK;
+}
+
+// CTAs per cluster for the forward / data-gradient kernels: every weight tile is fetched once per cluster (each CTA
+// multicasts 1 / C of it), which is what takes these kernels off the L2 -> SM bandwidth limit.  Needs 128-wide tiles
+// throughout the launch (slices of whole swizzle atoms) and at least C row tiles.  SWR_TC_CLUSTER=1|2|4 overrides.
+static int t2_pick_cluster(bool all128, int mtiles) {
+  static int want = [] { const char* e = getenv("SWR_TC_CLUSTER"); const int v = e ? atoi(e) : 2; return (v == 1 || v == 2 || v == 4) ? v : 2; }();
+  int c = all128 ? want : 1;
+  while (c > 1 && mtiles < c) c >>= 1;
+  return c;
+}
+template <class K>
+static int t2_launch(K kernel, int n_tiles, int cluster, size_t smem, const Tc2Params& p, cudaStream_t st, const char* name) {
+  const int sms = t2_num_sms();
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(T2_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int max_clusters = sms / cluster;
+  if (cluster > 1) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    // clusters that can be resident at once (GPC boundaries strand a few SMs at cluster size 4)
+    static thread_local int cached[5] = {0, 0, 0, 0, 0};
+    if (!cached[cluster]) {
+      cfg.gridDim = dim3(sms / cluster * cluster, 1, 1);
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = max_clusters; }
+      cached[cluster] = n;
+    }
+    max_clusters = min(max_clusters, cached[cluster]);
+  }
+  cfg.gridDim = dim3(min(n_tiles, max_clusters) * cluster, 1, 1);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
+  if (e != cudaSuccess) { set_error("launch of %s failed: %s", name, cudaGetErrorString(e)); return SWR_ERR_CUDA; }
+  count_launch();
   return SWR_OK;
 }
 
@@ -982,26 +1220,54 @@ int launch_fc_tc2_fwd(const FcGroup* groups, int n_groups, int64_t B, cudaStream
   Tc2Params p{};
   p.n_groups = n_groups; p.B = (int)B; p.inv_count = 1.0f / (float)B;
   const int mtiles = ceil_div(B, T2_BM);
+  bool all128 = true;
+  for (int g = 0; g < n_groups; ++g) all128 = all128 && t2_pick_nt(groups[g].Y.n) == 128;
+  const int C = t2_pick_cluster(all128, mtiles);
+  p.cluster = C;
   int tiles = 0, kmax = 0, nt_max = 0, flush = 1 << 30;
   for (int g = 0; g < n_groups; ++g) {
     p.g[g] = groups[g];
     const int N = groups[g].Y.n, K = groups[g].A.n;
     p.nt[g] = t2_pick_nt(N);
     p.tile_start[g] = tiles;
-    tiles += mtiles * ceil_div(N, p.nt[g]);
+    tiles += ceil_div(mtiles, C) * ceil_div(N, p.nt[g]);
     kmax = max(kmax, K); nt_max = max(nt_max, p.nt[g]);
     flush = min(flush, t2_flush_for(p.nt[g]));
-    int rc = t2_make_map(&p.tm[g], groups[g].img_f, N, t2_round_up(K, 32), p.nt[g]);
+    int rc = C == 1 ? t2_make_map(&p.tm0[g], groups[g].img_f, N, t2_round_up(K, 32), p.nt[g])
+                    : t2_make_map(&p.tm0[g], groups[g].img_f, N, t2_round_up(K, 32), p.nt[g] / C, 1);
+    if (rc) return rc;
+    rc = t2_make_act_map(&p.tm1[g], groups[g].A.raw, (int)B, K, groups[g].A.ld, 32, T2_BM, true);
     if (rc) return rc;
   }
   p.tile_start[n_groups] = tiles; p.n_tiles = tiles; p.flush = flush;
   size_t smem = 0;
-  int rc = t2_plan_smem(p, nt_max, 3 * sizeof(float) * (size_t)t2_round_up(kmax, KBLK), 0, ceil_div(kmax, KBLK), &smem);
+  int rc = t2_plan_smem(p, 2 * (size_t)nt_max * 128, T2_RAW_BYTES, 3 * sizeof(float) * (size_t)t2_round_up(kmax, KBLK), 0, &smem);
   if (rc) return rc;
   rc = t2_set_smem(fc_tc2_kernel<T2_FWD>, smem);
   if (rc) return rc;
-  fc_tc2_kernel<T2_FWD><<<min(tiles, t2_num_sms()), T2_THREADS, smem, st>>>(p);
-  SWR_LAUNCH_OK("fc_tc2_kernel<fwd>");
+  static const bool debug = getenv("SWR_TC_DEBUG") != nullptr;
+  static long long* dbg_dev = nullptr;
+  if (debug) {
+    if (!dbg_dev) cudaMalloc(&dbg_dev, 512 * sizeof(long long));
+    cudaMemsetAsync(dbg_dev, 0, 512 * sizeof(long long), st);
+    p.dbg = dbg_dev;
+  }
+  rc = t2_launch(fc_tc2_kernel<T2_FWD>, tiles, C, smem, p, st, "fc_tc2_kernel<fwd>");
+  if (rc) return rc;
+  if (debug) {
+    long long h[512];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
+    const long long t0 = h[126];
+    fprintf(stderr, "[tc2 fwd dbg] tiles=%d cluster=%d nt0=%d sb=%d sr=%d flush=%d setup=%lld\n", tiles, C, p.nt[0], p.sb, p.sr, p.flush, h[127] - t0);
+    const char* names[4] = {"tma", "mma", "stg", "epi"};
+    for (int r = 0; r < 4; ++r) {
+      fprintf(stderr, "  %s:", names[r]);
+      for (int i = 0; i < 126 && h[r * 128 + i]; ++i) fprintf(stderr, " %lld", h[r * 128 + i] - t0);
+      if (r == 2 || r == 3) fprintf(stderr, " | end %lld", h[r * 128 + 127] - t0);
+      fprintf(stderr, "\n");
+    }
+  }
   return SWR_OK;
 }
 
@@ -1041,29 +1307,41 @@ int launch_fc_tc2_dgrad(const FcGroup* groups, const int* dst_group_in, int n_ds
   }
   p.n_dst = n_dst;
   for (int d = 0; d <= n_dst; ++d) p.dst_group[d] = dst_group[d];
+  bool all128 = true;
+  for (int d = 0; d < n_dst; ++d) all128 = all128 && t2_pick_nt(groups[dst_group[d]].A.n) == 128;
+  const int C = t2_pick_cluster(all128, mtiles);
+  p.cluster = C;
   int tiles = 0, nkb_max = 0, nt_max = 0, flush = 1 << 30;
   for (int d = 0; d < n_dst; ++d) {
     const int kd = groups[dst_group[d]].A.n;
     p.nt[d] = t2_pick_nt(kd);
     p.dst_tile[d] = tiles;
-    tiles += mtiles * ceil_div(kd, p.nt[d]);
+    tiles += ceil_div(mtiles, C) * ceil_div(kd, p.nt[d]);
     nkb_max = max(nkb_max, p.tile_start[dst_group[d + 1]] - p.tile_start[dst_group[d]]);
     nt_max = max(nt_max, p.nt[d]);
     flush = min(flush, t2_flush_for(p.nt[d]));
     for (int g = dst_group[d]; g < dst_group[d + 1]; ++g) {
-      int rc = t2_make_map(&p.tm[g], groups[g].img_d, groups[g].A.n, t2_round_up(groups[g].Y.n, 32), p.nt[d]);
+      const FcGroup& G = groups[g];
+      // the image holds every input feature of the layer (k_full rows); the destination may use only its first A.n
+      int rc = C == 1 ? t2_make_map(&p.tm0[g], G.img_d, G.k_full, t2_round_up(G.Y.n, 32), p.nt[d])
+                      : t2_make_map(&p.tm0[g], G.img_d, G.k_full, t2_round_up(G.Y.n, 32), p.nt[d] / C, 1);
       if (rc) return rc;
+      rc = t2_make_act_map(&p.tm1[g], G.Y.dz, (int)B, G.Y.n, G.Y.ld, 32, T2_BM, true);
+      if (rc) return rc;
+      if (G.Y.norm.mode == SWR_NORM_BATCH) {
+        rc = t2_make_act_map(&p.tm2[g], G.Y.raw, (int)B, G.Y.n, G.Y.ld, 32, T2_BM, true);
+        if (rc) return rc;
+      }
     }
   }
   p.dst_tile[n_dst] = tiles; p.n_tiles = tiles; p.flush = flush;
   size_t smem = 0;
-  int rc = t2_plan_smem(p, nt_max, 3 * sizeof(float) * (size_t)nkb_max * KBLK, 4 * sizeof(float) * (size_t)nt_max, nkb_max, &smem);
+  int rc = t2_plan_smem(p, 2 * (size_t)nt_max * 128, 2 * (size_t)T2_RAW_BYTES, 3 * sizeof(float) * (size_t)nkb_max * KBLK,
+                        4 * sizeof(float) * (size_t)nt_max, &smem);
   if (rc) return rc;
   rc = t2_set_smem(fc_tc2_kernel<T2_DGRAD>, smem);
   if (rc) return rc;
-  fc_tc2_kernel<T2_DGRAD><<<min(tiles, t2_num_sms()), T2_THREADS, smem, st>>>(p);
-  SWR_LAUNCH_OK("fc_tc2_kernel<dgrad>");
-  return SWR_OK;
+  return t2_launch(fc_tc2_kernel<T2_DGRAD>, tiles, C, smem, p, st, "fc_tc2_kernel<dgrad>");
 }
 
 int launch_fc_tc2_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st) {
@@ -1071,11 +1349,20 @@ int launch_fc_tc2_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStre
   p.n_groups = n_groups; p.B = (int)B; p.inv_count = 1.0f / (float)B;
   int base = 0, nt_max = 0, flush = 1 << 30;
   for (int g = 0; g < n_groups; ++g) {
-    p.g[g] = groups[g];
-    p.nt[g] = max(32, t2_pick_nt(groups[g].A.n));      // the MN-major column operand is staged in 32-wide groups
-    base += ceil_div(groups[g].Y.n, T2_BM) * ceil_div(groups[g].A.n, p.nt[g]);
+    const FcGroup& G = groups[g];
+    p.g[g] = G;
+    p.nt[g] = max(32, t2_pick_nt(G.A.n));      // the MN-major column operand is staged in 32-wide groups
+    base += ceil_div(G.Y.n, T2_BM) * ceil_div(G.A.n, p.nt[g]);
     nt_max = max(nt_max, p.nt[g]);
     flush = min(flush, t2_flush_for(p.nt[g]));
+    int rc = t2_make_act_map(&p.tm0[g], G.Y.dz, (int)B, G.Y.n, G.Y.ld, T2_BM, 32, false);
+    if (rc) return rc;
+    if (G.Y.norm.mode == SWR_NORM_BATCH) {
+      rc = t2_make_act_map(&p.tm1[g], G.Y.raw, (int)B, G.Y.n, G.Y.ld, T2_BM, 32, false);
+      if (rc) return rc;
+    }
+    rc = t2_make_act_map(&p.tm2[g], G.A.raw, (int)B, G.A.n, G.A.ld, p.nt[g], 32, false);
+    if (rc) return rc;
   }
   // split the batch so that the launch has about two tiles per SM; keep >= 4 k-blocks (128 rows) per split
   const int sms = t2_num_sms();
@@ -1090,13 +1377,12 @@ int launch_fc_tc2_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStre
   }
   p.tile_start[n_groups] = tiles; p.n_tiles = tiles; p.flush = flush;
   size_t smem = 0;
-  int rc = t2_plan_smem(p, nt_max, 3 * sizeof(float) * (size_t)nt_max, 0, ceil_div(rows, KBLK), &smem);
+  int rc = t2_plan_smem(p, 2 * (size_t)nt_max * 128, 2 * (size_t)T2_RAW_BYTES + 32 * (size_t)nt_max * 4, 3 * sizeof(float) * (size_t)nt_max, 0, &smem);
   if (rc) return rc;
   rc = t2_set_smem(fc_tc2_wgrad_kernel, smem);
   if (rc) return rc;
-  fc_tc2_wgrad_kernel<<<min(tiles, sms), T2_THREADS, smem, st>>>(p);
-  SWR_LAUNCH_OK("fc_tc2_wgrad_kernel");
-  return SWR_OK;
+  p.cluster = 1;
+  return t2_launch(fc_tc2_wgrad_kernel, tiles, 1, smem, p, st, "fc_tc2_wgrad_kernel");
 }
 
 }  // namespace swr

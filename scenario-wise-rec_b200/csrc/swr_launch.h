@@ -35,6 +35,7 @@ struct FcGroup {
   double* stats_out;    // [N][2] column moments of Y (train-mode BatchNorm), or null
   const float* img_f;   // presplit weight images (swr_fc_tc2.cu): [2][N][K32] forward, [2][K][N32] data gradient; null = none
   const float* img_d;
+  int k_full;           // input width of the layer's weight (A.n may be narrowed to the columns that receive a data gradient)
   int w_layout; int ldw;
   int e_act; float e_scale;   // epilogue activation for layers without a norm (GateNU)
   int flags;            // bit0: A needs a gradient, bit1: accumulate into A.dz

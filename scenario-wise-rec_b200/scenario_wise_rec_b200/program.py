@@ -383,6 +383,7 @@ class ProgramBuilder:
         s[28], s[29], s[30], s[31] = self.grad(g.W), self.grad(g.W2), self.grad(g.b), self.grad(g.b2)
         s[10], s[11] = g.img_f, g.img_d
         r["i"][8], r["i"][9], r["i"][10], r["i"][11] = g.layout, int(g.W.stride(0)), g.e_act, flags
+        r["i"][13] = g.src.n           # full input width (a dgrad record may narrow i[1] to the columns that get a gradient)
         r["f"][4] = g.e_scale
         return r
 

@@ -11,7 +11,7 @@ for step in "$@"; do
     bench) timeout 900 python bench.py --steps 100 --warmup 10 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err ;;
     benchq) timeout 600 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err ;;
     ref) timeout 600 python bench.py --impl reference --steps 10 --warmup 2 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench_ref.json ;;
-    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${TAG}_launches.csv \
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:^(fc_|adam|bce|bn_|gather|scatter|head_|pool_|ew_|ln_|mix_|bmv_|select_|sumgrad|colstats)" -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
         python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1 ;;
     full:*) IFS=: read -r _ KRE CNT SKIP <<< "$step"
         timeout 1200 ncu --set full --clock-control none --import-source on -k regex:${KRE} -s ${SKIP:-40} -c ${CNT:-3} -f -o gpurun_out/${TAG}_prof \
