@@ -161,6 +161,9 @@ typedef enum swr_op_kind {
   SWR_OP_FC_PRESPLIT = 27,/* effective weights W (.) W2 -> hi / lo TF32 images (both orientations) that the
                              tcgen05 FC kernels read through TMA; sub-records = FC group records whose
                              s[10] / s[11] name the forward / data-gradient image buffers           */
+  SWR_OP_ADAM_ROWS = 28,  /* row-lazy Adam on embedding tables: i[1] = 0 catch-up of the batch's rows before the
+                             gather, 1 update after the scatter (same trajectory as the dense sweep)    */
+  SWR_OP_ADAM_FLUSH = 29, /* replay every postponed row update of the listed tables up to the current step    */
   SWR_OP_GROUP = 100      /* a group record belonging to the preceding header          */
 } swr_op_kind;
 

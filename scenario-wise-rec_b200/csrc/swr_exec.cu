@@ -121,6 +121,24 @@ static int run_presplit(const swr_rec_t* subs, int n, Ctx& c, cudaStream_t st) {
   return launch_fc_presplit(groups.data(), n, st);
 }
 
+static int run_lazy_adam(const swr_rec_t& h, const swr_rec_t* subs, bool flush, Ctx& c, cudaStream_t st) {
+  std::vector<LazyField> f(h.n_sub);
+  for (int i = 0; i < h.n_sub; ++i) {
+    const swr_rec_t& r = subs[i];
+    f[i].p = static_cast<float*>(c.slot(r.s[0])); f[i].g = static_cast<float*>(c.slot(r.s[1]));
+    f[i].m = static_cast<float*>(c.slot(r.s[2])); f[i].v = static_cast<float*>(c.slot(r.s[3]));
+    f[i].last = static_cast<int*>(c.slot(r.s[4])); f[i].claim = static_cast<int*>(c.slot(r.s[5]));
+    f[i].idx = c.slot(r.s[6]); f[i].idx_dtype = r.i[2];
+    f[i].vocab = ((int64_t)(uint32_t)r.i[0]) | ((int64_t)r.i[1] << 32); f[i].E = r.i[5];
+  }
+  if (!c.ok) return SWR_ERR_INVALID;
+  const float* hyper = static_cast<const float*>(c.slot(h.s[0]));
+  const int32_t* ctrl = static_cast<const int32_t*>(c.slot(h.s[1]));
+  float4* hist = static_cast<float4*>(c.slot(h.s[2]));
+  if (flush) return launch_adam_flush(f.data(), h.n_sub, hyper, ctrl, hist, st);
+  return launch_adam_rows(f.data(), h.n_sub, h.i[0], hyper, ctrl, hist, h.i[1], st);
+}
+
 static int run_gather(const swr_rec_t& h, const swr_rec_t* subs, Ctx& c, cudaStream_t st) {
   const int n = h.n_sub;
   std::vector<const float*> tables; std::vector<int64_t> vocab; std::vector<const void*> idx; std::vector<int32_t> idt, E;
@@ -395,6 +413,8 @@ SWR_API int swr_program_run(const swr_rec_t* recs, int32_t n_recs, void* const* 
                         static_cast<float*>(c.slot(h.s[3])), static_cast<const int32_t*>(c.slot(h.s[4])), h.i[2], h.i[0],
                         h.f[0] != 0.f ? h.f[0] : 1.f, st);
         break;
+      case SWR_OP_ADAM_ROWS: rc = run_lazy_adam(h, subs, false, c, st); break;
+      case SWR_OP_ADAM_FLUSH: rc = run_lazy_adam(h, subs, true, c, st); break;
       case SWR_OP_ADAM:
         rc = launch_adam(static_cast<float*>(c.slot(h.s[0])), static_cast<float*>(c.slot(h.s[1])), static_cast<float*>(c.slot(h.s[2])),
                          static_cast<float*>(c.slot(h.s[3])), static_cast<const float*>(c.slot(h.s[4])),

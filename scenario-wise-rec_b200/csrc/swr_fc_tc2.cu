@@ -492,7 +492,6 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
     // through its own transpose tile (so the registers of a pass are dead before its row loop runs).
     const int e = warp - T2_NSTAGER, q = warp & 3, ch = e >> 2;
     uint32_t acc_it = 0;
-    int ev3 = 0;
     for (int t = t_begin; t < t_end; ++t) {
       float acc[64];
 #pragma unroll
@@ -555,13 +554,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
         if (pc0 >= T.NT) break;                      // uniform over the group
         const int pc = min(32, T.NT - pc0);
         const int nvalid = min(max(Nend - (T.n0 + pc0), 0), pc);
-        if (e == 0 && lane == 0) { T2_STAMP(3, ev3); ++ev3; }
         named_bar(bar_g, 128);                       // the group is done with the previous contents of ot / red
-        if (e == 0 && lane == 0) { T2_STAMP(3, ev3); ++ev3; }
         t2_acc_to_smem(ot_s, arow, sp, pc, acc);
-        if (e == 0 && lane == 0) { T2_STAMP(3, ev3); ++ev3; }
         named_bar(bar_g, 128);
-        if (e == 0 && lane == 0) { T2_STAMP(3, ev3); ++ev3; }
         const int nv = nvalid - c4;                  // valid components of this lane's column quad (<= 0: none)
         const int n = T.n0 + pc0 + c4;               // first output column of the quad
         const uint32_t my_ot = ot_s + (uint32_t)(row_base * T2_OT_LD + c4) * 4u;   // + i * 4 rows
@@ -580,9 +575,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
             const float4 r0 = lds128(ot_s + (uint32_t)c4 * 4u);      // row 0 of the tile: always a valid batch row
             if (G.e_act == SWR_ACT_NONE && vec) {   // the common case, branch-free per row
               const float4 y0 = make_float4(r0.x + bias.x, r0.y + bias.y, r0.z + bias.z, r0.w + bias.w);
-              if (y0.x == 1234.5f) s1.x = 1.f;
-              if (e == 0 && lane == 0) { T2_STAMP(3, ev3); ++ev3; }
-#pragma unroll 2
+      #pragma unroll 2
               for (int i = 0; i < rows_here; ++i) {
                 const float4 a = lds128(my_ot + (uint32_t)(4 * i * T2_OT_LD) * 4u);
                 const float4 y = make_float4(a.x + bias.x, a.y + bias.y, a.z + bias.z, a.w + bias.w);
@@ -679,7 +672,6 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
             }
           }
         }
-        if (e == 0 && lane == 0) { T2_STAMP(3, ev3); ++ev3; }
         const bool want_stats = (MODE == T2_FWD) ? (G.stats_out != nullptr) : (has_norm && D.dstats != nullptr);
         if (want_stats) {           // uniform over the group
 #pragma unroll
@@ -693,10 +685,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
             *reinterpret_cast<float4*>(red + (0 * 4 + q) * 32 + c4) = s1;
             *reinterpret_cast<float4*>(red + (1 * 4 + q) * 32 + c4) = s2;
           }
-          if (e == 0 && lane == 0) { T2_STAMP(3, ev3); ++ev3; }
-          named_bar(bar_g, 128);
-          if (e == 0 && lane == 0) { T2_STAMP(3, ev3); ++ev3; }
-          if (gtid < nvalid && cnt_rows > 0) {      // one thread per column: fp32 sum over the group's warps, widened once
+            named_bar(bar_g, 128);
+            if (gtid < nvalid && cnt_rows > 0) {      // one thread per column: fp32 sum over the group's warps, widened once
             const float S1 = red[gtid] + red[32 + gtid] + red[64 + gtid] + red[96 + gtid];
             const float S2 = red[128 + gtid] + red[160 + gtid] + red[192 + gtid] + red[224 + gtid];
             const int col = T.n0 + pc0 + gtid;
@@ -710,8 +700,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
               atomicAdd(D.dstats + 2 * col + 1, (double)S2);
             }
           }
-          if (e == 0 && lane == 0) { T2_STAMP(3, ev3); ++ev3; }
-          }
+            }
       }
     }
   }
@@ -1142,9 +1131,9 @@ static int t2_set_smem(K kernel, size_t bytes) {
 // shared-memory plan: ring B [sb][stage_b] | ring R [sr][stage_r] | coef | ccs | ot | red
 static int t2_plan_smem(Tc2Params& p, size_t stage_b, size_t stage_r, size_t coef_bytes, size_t ccs_bytes, size_t* smem_bytes) {
   const size_t fixed = ((coef_bytes + 15) & ~(size_t)15) + ((ccs_bytes + 15) & ~(size_t)15) + T2_OT_BYTES + T2_RED_BYTES;
-  // Stay inside the 196 KB shared-memory carve-out: the next step (228 KB) leaves the SM without L1, and the few
-  // registers the epilogue spills (64 running sums per thread in a 96-register budget) then cost an L2 round trip each.
-  static const size_t budget = [] { const char* e = getenv("SWR_TC_SMEM_KB"); return (size_t)(e ? atoi(e) : 195) * 1024 - 1024; }();
+  // 227 KB opt-in maximum minus static shared memory and alignment slack (SWR_TC_SMEM_KB: experiments with the
+  // 196 KB carve-out, which leaves 32 KB of L1, showed no gain)
+  static const size_t budget = [] { const char* e = getenv("SWR_TC_SMEM_KB"); return (size_t)(e ? atoi(e) : 224) * 1024 - 1024; }();
   static const int pref[][2] = {{4, 4}, {4, 3}, {3, 3}, {4, 2}, {3, 2}, {2, 3}, {2, 2}};
   int sb = 0, sr = 0;
   for (auto& c : pref)
@@ -1162,10 +1151,12 @@ static int t2_plan_smem(Tc2Params& p, size_t stage_b, size_t stage_r, size_t coe
 }
 
 // CTAs per cluster for the forward / data-gradient kernels: every weight tile is fetched once per cluster (each CTA
-// multicasts 1 / C of it), which is what takes these kernels off the L2 -> SM bandwidth limit.  Needs 128-wide tiles
-// throughout the launch (slices of whole swizzle atoms) and at least C row tiles.  SWR_TC_CLUSTER=1|2|4 overrides.
+// multicasts 1 / C of it).  Needs 128-wide tiles throughout the launch (slices of whole swizzle atoms) and at least C row
+// tiles.  Measured on cfg2 (profiles/r02_fc_tc2_notes.md): no gain at C = 2 or 4 -- the kernels are bound by shared-memory
+// bandwidth (TMA writes + three operand reads per k-step + the stagers' reads), not by L2 -> SM traffic -- so the default
+// is 1; SWR_TC_CLUSTER=2|4 enables it.
 static int t2_pick_cluster(bool all128, int mtiles) {
-  static int want = [] { const char* e = getenv("SWR_TC_CLUSTER"); const int v = e ? atoi(e) : 2; return (v == 1 || v == 2 || v == 4) ? v : 2; }();
+  static int want = [] { const char* e = getenv("SWR_TC_CLUSTER"); const int v = e ? atoi(e) : 1; return (v == 1 || v == 2 || v == 4) ? v : 1; }();
   int c = all128 ? want : 1;
   while (c > 1 && mtiles < c) c >>= 1;
   return c;

@@ -160,4 +160,15 @@ int launch_bce(const float* pred, const void* label, int label_dtype, float* gou
                int ring, int64_t B, float gscale, cudaStream_t st);
 int launch_adam(float* p, float* g, float* m, float* v, const float* hyper, int64_t n, int zero_grad, cudaStream_t st);
 
+// row-lazy Adam for embedding tables (swr_train.cu): catch-up before the gather, update after the scatter, flush
+struct LazyField {
+  float* p; float* g; float* m; float* v;     // [vocab, E] views into the flat arenas
+  int* last; int* claim;                      // [vocab]
+  const void* idx; int idx_dtype;             // index column [B]
+  int64_t vocab; int E;
+};
+int launch_adam_rows(const LazyField* fields, int n_fields, int64_t B, const float* hyper, const int32_t* ctrl, float4* hist, int phase,
+                     cudaStream_t st);
+int launch_adam_flush(const LazyField* fields, int n_fields, const float* hyper, const int32_t* ctrl, const float4* hist, cudaStream_t st);
+
 }  // namespace swr

@@ -99,4 +99,142 @@ int launch_adam(float* p, float* g, float* m, float* v, const float* hyper, int6
   return SWR_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// Row-lazy Adam for embedding tables: the same trajectory as the dense sweep, without touching every row every step.
+//
+// torch.optim.Adam on a dense table gradient (ctr_trainer.py:50-52,73) updates EVERY row at every step: a row no sample
+// looked up has g = 0 and still moves (weight decay pulls it, its moments decay).  Those updates depend on nothing but the
+// row's own (p, m, v) and the step's scalars, so they can be postponed and replayed later with bit-identical results:
+//   * last[r]   the step up to which row r is current,
+//   * hist[s]   the scalars of step s (lr / bias-correction-1, 1 / sqrt(bias-correction-2), weight decay), appended by
+//               the update kernel of step s,
+//   * catch-up  before the forward gather, every row of the batch is replayed to step t - 1 (g = 0 steps),
+//   * update    after the backward scatter, every row of the batch gets step t with its gradient, and its gradient row
+//               is zeroed again (the dense gradient arena stays all-zero between steps: no O(vocab) memset),
+//   * flush     every row is replayed to the current step: bounds the replay length, and makes the parameters readable
+//               by anything outside the fused step (state_dict, evaluation, checkpoints).
+// A row is claimed for a phase with atomicMax on claim[r] (2 t for the catch-up, 2 t + 1 for the update), so duplicate
+// lookups of one row inside a batch do the work once.  adam_elem is the dense kernel's own update: same instructions,
+// same rounding.
+// ---------------------------------------------------------------------------------------
+constexpr int kLazyMax = 48;
+struct LazyParams {
+  LazyField f[kLazyMax];
+  int n_fields; int B;
+  const float* hyper;       // lr/bc1, b1, b2, eps, wd, 1/sqrt(bc2) of the current step
+  const int32_t* ctrl;      // ctrl[1] = current step t (1-based), ctrl[2] = first step of the history table
+  float4* hist;             // [capacity] scalars per step, index s - ctrl[2]
+};
+
+__device__ __forceinline__ void lazy_replay(float& P, float& M, float& V, int from, int to, const float4* hist, int base,
+                                            float b1, float b2, float eps) {
+  for (int s = from; s <= to; ++s) {          // steps the row sat out: zero gradient
+    const float4 h = __ldg(hist + (s - base));
+    adam_elem(P, 0.f, M, V, h.x, b1, b2, eps, h.z, h.y);
+  }
+}
+
+// phase 0: catch-up to t - 1;  phase 1: (catch-up +) step t with the gradient row, gradient row zeroed
+template <int PHASE>
+__global__ void __launch_bounds__(256) adam_rows_kernel(const __grid_constant__ LazyParams p) {
+  const int t = p.ctrl[1], base = p.ctrl[2];
+  const float b1 = __ldg(p.hyper + 1), b2 = __ldg(p.hyper + 2), eps = __ldg(p.hyper + 3);
+  if (PHASE == 1 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+    p.hist[t - base] = make_float4(__ldg(p.hyper + 0), __ldg(p.hyper + 5), __ldg(p.hyper + 4), 0.f);
+  const LazyField& F = p.f[blockIdx.y];
+  const int E = F.E, lanes = E < 32 ? E : 32;            // E <= 32: one row per `E` lanes; wider rows: a warp strides over it
+  const int per_warp = 32 / lanes;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / lanes, l = lane - sub * lanes;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int b0 = warp_global * per_warp; b0 < p.B; b0 += n_warps * per_warp) {
+    const int b = b0 + sub;
+    int64_t r = -1;
+    int old = 0x7fffffff;
+    if (b < p.B && sub < per_warp) {
+      r = load_index(F.idx, F.idx_dtype, b);
+      if (r < 0 || r >= F.vocab) r = -1;
+      if (r >= 0 && l == 0) old = atomicMax(F.claim + r, 2 * t + PHASE);
+    }
+    old = __shfl_sync(0xffffffffu, old, (sub * lanes) & 31);
+    const bool own = r >= 0 && old < 2 * t + PHASE;       // in range, and no other lookup of the batch owns the row
+    if (own) {
+      const int last = F.last[r];
+      for (int e = l; e < E; e += lanes) {
+        const int64_t o = r * E + e;
+        float P = F.p[o], M = F.m[o], V = F.v[o];
+        lazy_replay(P, M, V, last + 1, t - 1, p.hist, base, b1, b2, eps);
+        if (PHASE == 1) {
+          adam_elem(P, F.g[o], M, V, __ldg(p.hyper + 0), b1, b2, eps, __ldg(p.hyper + 4), __ldg(p.hyper + 5));
+          F.g[o] = 0.f;
+        }
+        F.p[o] = P; F.m[o] = M; F.v[o] = V;
+      }
+    }
+    __syncwarp();
+    if (own && l == 0) F.last[r] = (PHASE == 1) ? t : t - 1;
+  }
+}
+
+// every row of one table to step t (ctrl[1]); one thread per element
+__global__ void __launch_bounds__(256) adam_flush_kernel(float* __restrict__ P, float* __restrict__ M, float* __restrict__ V,
+                                                         int* __restrict__ last, int64_t vocab, int E, const float* __restrict__ hyper,
+                                                         const int32_t* __restrict__ ctrl, const float4* __restrict__ hist) {
+  const int t = ctrl[1], base = ctrl[2];
+  const float b1 = __ldg(hyper + 1), b2 = __ldg(hyper + 2), eps = __ldg(hyper + 3);
+  const int64_t n = vocab * E;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / E;
+    const int from = last[r] + 1;
+    if (from > t) continue;
+    float p = P[i], m = M[i], v = V[i];
+    lazy_replay(p, m, v, from, t, hist, base, b1, b2, eps);
+    P[i] = p; M[i] = m; V[i] = v;
+  }
+}
+__global__ void __launch_bounds__(256) adam_flush_mark_kernel(int* __restrict__ last, int64_t vocab, const int32_t* __restrict__ ctrl) {
+  const int t = ctrl[1];
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < vocab; r += (int64_t)gridDim.x * blockDim.x)
+    if (last[r] < t) last[r] = t;
+}
+
+int launch_adam_rows(const LazyField* fields, int n_fields, int64_t B, const float* hyper, const int32_t* ctrl, float4* hist, int phase,
+                     cudaStream_t st) {
+  if (n_fields <= 0 || B <= 0) return SWR_OK;
+  if (!hyper || !ctrl || !hist) { set_error("adam_rows: null operand"); return SWR_ERR_INVALID; }
+  for (int o = 0; o < n_fields; o += kLazyMax) {
+    LazyParams p{};
+    p.n_fields = n_fields - o < kLazyMax ? n_fields - o : kLazyMax;
+    for (int i = 0; i < p.n_fields; ++i) {
+      p.f[i] = fields[o + i];
+      if (!p.f[i].p || !p.f[i].g || !p.f[i].m || !p.f[i].v || !p.f[i].last || !p.f[i].claim || !p.f[i].idx) { set_error("adam_rows: null field operand"); return SWR_ERR_INVALID; }
+    }
+    p.B = (int)B; p.hyper = hyper; p.ctrl = ctrl; p.hist = hist;
+    const int E0 = p.f[0].E, per_block = 8 * (E0 < 32 ? 32 / E0 : 1);
+    int gx = (int)((B + per_block - 1) / per_block);
+    if (gx > 4 * 148) gx = 4 * 148;
+    if (phase == 0) adam_rows_kernel<0><<<dim3(gx, p.n_fields), 256, 0, st>>>(p);
+    else adam_rows_kernel<1><<<dim3(gx, p.n_fields), 256, 0, st>>>(p);
+    SWR_LAUNCH_OK("adam_rows_kernel");
+  }
+  return SWR_OK;
+}
+
+int launch_adam_flush(const LazyField* fields, int n_fields, const float* hyper, const int32_t* ctrl, const float4* hist, cudaStream_t st) {
+  for (int i = 0; i < n_fields; ++i) {
+    const LazyField& F = fields[i];
+    const int64_t n = F.vocab * F.E;
+    if (n <= 0) continue;
+    int grid = (int)((n + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    adam_flush_kernel<<<grid, 256, 0, st>>>(F.p, F.m, F.v, F.last, F.vocab, F.E, hyper, ctrl, hist);
+    SWR_LAUNCH_OK("adam_flush_kernel");
+    int g2 = (int)((F.vocab + 255) / 256);
+    if (g2 > 148 * 8) g2 = 148 * 8;
+    adam_flush_mark_kernel<<<g2, 256, 0, st>>>(F.last, F.vocab, ctrl);
+    SWR_LAUNCH_OK("adam_flush_mark_kernel");
+  }
+  return SWR_OK;
+}
+
 }  // namespace swr

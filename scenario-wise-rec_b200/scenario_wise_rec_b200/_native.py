@@ -27,7 +27,7 @@ OP_POOL_FWD, OP_POOL_BWD, OP_HEAD_FWD, OP_HEAD_BWD = 8, 9, 10, 11
 OP_BN_UPDATE, OP_BN_PGRAD, OP_GROUP = 12, 13, 100
 OP_EW_FWD, OP_EW_BWD, OP_SUMGRAD, OP_SELECT_FWD, OP_SELECT_BWD = 14, 15, 16, 17, 18
 OP_LN_FWD, OP_LN_BWD, OP_MIX_FWD, OP_MIX_BWD, OP_BMV_FWD, OP_BMV_BWD = 19, 20, 21, 22, 23, 24
-OP_BCE, OP_ADAM, OP_FC_PRESPLIT = 25, 26, 27
+OP_BCE, OP_ADAM, OP_FC_PRESPLIT, OP_ADAM_ROWS, OP_ADAM_FLUSH = 25, 26, 27, 28, 29
 EW_MUL, EW_ADD, EW_COPY = 0, 1, 2
 HEAD_SIG_SELECT_ADD, HEAD_SELECT_SIG, HEAD_NO_SELECT = 0, 1, 2
 NORM_NONE, NORM_BATCH, NORM_RUNNING = 0, 1, 2

@@ -104,6 +104,15 @@ class CTRTrainer(object):
             if self._flat is None:
                 self._flat = fs.flat
                 self.optimizer.register_state_dict_pre_hook(lambda _opt: self._flat is not None and self._flat.publish_step())
+                if fs.flat.lazy is not None and not getattr(self.model, "_swr_lazy_hooks", False):
+                    # row-lazy Adam: whatever reads the tables outside the fused step first gets every row replayed to
+                    # the current step (generic forward = evaluation / prediction, state_dict = checkpoints, EarlyStopper)
+                    def flush(*_a, **_k):
+                        if self._flat is not None:
+                            self._flat.flush_lazy()
+                    self.model.register_forward_pre_hook(flush)
+                    self.model.register_state_dict_pre_hook(flush)
+                    self.model._swr_lazy_hooks = True
             self._steps[key] = fs
         return fs
 

@@ -94,6 +94,13 @@ class FlatArenas:
         self.step = step
         self.optimizer = optimizer
         self._ptr0 = [p.data_ptr() for p in self.params[:1] + self.params[-1:]]
+        # row-lazy Adam over the replicated tables (single process; SWR_LAZY_ADAM=0 keeps the dense sweep)
+        self.lazy = None
+        import torch.distributed as dist
+        single = not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+        tables = [(p, off, int(p.shape[0]), int(p.shape[1])) for p, a, off, n in entries if a == "emb" and p.dim() == 2]
+        if single and tables and os.environ.get("SWR_LAZY_ADAM", "1") != "0" and len(tables) == sum(1 for _p, a, *_ in entries if a == "emb"):
+            self.lazy = LazyTables(self, tables)
 
     def shard_grad(self, shard_param) -> torch.Tensor:
         for p, _a, off, n in self.shards:
@@ -110,10 +117,60 @@ class FlatArenas:
         strip = lambda lst: [e for e in lst if e[1] != "virt"]      # noqa: E731  (virtual tables are per batch size)
         return strip(cur) == strip(self.layout)
 
+    def flush_lazy(self):
+        """Bring every table row to the current step (no-op when nothing is postponed)."""
+        if self.lazy is not None and self.lazy.dirty and self.flush_fn is not None:
+            self.flush_fn()
+
+    flush_fn = None
+
     def publish_step(self):
         """Write the step counter into ``optimizer.state`` (kept lazily: one Python loop per epoch, not per step)."""
+        self.flush_lazy()
         for p in self.params:
             self.optimizer.state[p]["step"].fill_(float(self.step))
+
+
+class LazyTables:
+    """State of the row-lazy Adam over the embedding tables of the ``emb`` arena (csrc/swr_train.cu).
+
+    ``torch.optim.Adam`` on dense table gradients (the reference, ctr_trainer.py:50-52,73) updates every row of every
+    table at every step; a row outside the batch has a zero gradient and still moves (weight decay, decaying moments).
+    Those zero-gradient updates depend only on the row itself and on the step's scalars, so they are postponed and
+    replayed -- with the dense kernel's own arithmetic, bit for bit -- when the row is next looked up, every
+    ``flush_every`` steps, and whenever something outside the fused step reads the parameters (state_dict, evaluation,
+    the end of ``train_one_epoch``).  Per step the optimizer then touches the batch's rows instead of sweeping
+    O(vocab) bytes, and the dense gradient arena needs no memset (updated rows are zeroed as they are consumed)."""
+
+    HIST_CAP = 1 << 20          # steps of scalars kept on the device (16 B each); a flush re-bases the table
+
+    def __init__(self, flat: "FlatArenas", tables):
+        dev = flat.device
+        self.flat = flat
+        self.tables = tables                      # [(param, offset, vocab, E)] inside the emb arena
+        rows = sum(v for _p, _o, v, _e in tables)
+        self.row_off = {}
+        o = 0
+        for p_, _off, v, _e in tables:
+            self.row_off[id(p_)] = o
+            o += v
+        self.base = flat.step + 1                 # history index 0 = the first step taken from now on
+        self.last = torch.full((max(rows, 1),), flat.step, dtype=torch.int32, device=dev)
+        self.claim = torch.zeros(max(rows, 1), dtype=torch.int32, device=dev)
+        self.hist = torch.zeros(4 * self.HIST_CAP, dtype=torch.float32, device=dev)
+        self.flush_every = max(1, int(os.environ.get("SWR_LAZY_FLUSH", "32")))
+        self.dirty = False
+        self._flush_recs = None
+        self._flush_ptrs = None
+
+    def field_rec(self, ptrs_base: dict, table_param, idx_slot: int, dtype_code: int):
+        """(pointer list, ints) of one lookup column of ``table_param`` for an ADAM_ROWS sub-record."""
+        for p_, off, v, e in self.tables:
+            if p_ is table_param:
+                ro = self.row_off[id(p_)]
+                return ([ptrs_base["p"] + 4 * off, ptrs_base["g"] + 4 * off, ptrs_base["m"] + 4 * off, ptrs_base["v"] + 4 * off,
+                         self.last.data_ptr() + 4 * ro, self.claim.data_ptr() + 4 * ro], v, e)
+        raise KeyError("table is not in the emb arena")
 
 
 class LossHandle:
@@ -261,12 +318,68 @@ class FusedTrainStep:
         self.sparse_sync = self._setup_sparse_sync(prog, ptrs)
         gscale = 1.0 / self.sparse_sync["world"] if self.sparse_sync else 1.0
         bce = rec(N.OP_BCE, [self.B, N.DT_F32, RING], [prog.out_slot, X["label"], prog.gout_slot, X["loss"], X["ctrl"]], [gscale])
-        zeros = [rec(N.OP_ZERO, split(4 * gsize[a]), [self.arena_slots[a][1]]) for a in flat.size]
+        lazy = flat.lazy if (grad_sync is None and self.exchange is None) else None
+        self.lazy = lazy
+        if lazy is not None:
+            self.g["emb"].zero_()        # invariant of the lazy update: the dense table-gradient arena is all zero between steps
+        pre, post = [], []
+        if lazy is not None:
+            # one sub-record per index column that reads a table of the emb arena (taken from the K2 scatter records)
+            extra = []          # extra slot pointers appended behind the trainer slots
+            base = {"p": flat.p["emb"].data_ptr(), "g": self.g["emb"].data_ptr(), "m": flat.m["emb"].data_ptr(), "v": flat.v["emb"].data_ptr()}
+            by_grad_slot = {}
+            for p_, (a, off_, n_) in zip(prog.params, prog.param_arena):
+                if a == "emb":
+                    for i, d in enumerate(prog.slot_desc):
+                        if d[0] == "grad" and d[1] == "emb" and d[2] == off_:
+                            by_grad_slot[i] = p_
+            subs = []
+            recs_b_ = prog.recs_bwd
+            i = 0
+            while i < len(recs_b_):
+                ns = int(recs_b_[i]["n_sub"])
+                if int(recs_b_[i]["kind"]) == N.OP_SCATTER:
+                    for r in recs_b_[i + 1:i + 1 + ns]:
+                        tab = by_grad_slot.get(int(r["s"][0]))
+                        if tab is None:
+                            raise RuntimeError("scatter record of a table outside the emb arena")
+                        plist, vocab, E = lazy.field_rec(base, tab, int(r["s"][1]), int(r["i"][2]))
+                        sl = []
+                        for ptr in plist:
+                            extra.append(ptr)
+                            sl.append(len(ptrs) + len(extra) - 1)
+                        sub = rec(N.OP_GROUP, [*split(vocab), int(r["i"][2]), 0, 0, E], sl + [int(r["s"][1])])
+                        subs.append(sub)
+                i += 1 + ns
+            hist_slot = len(ptrs) + len(extra)
+            extra.append(lazy.hist.data_ptr())
+            ptrs = np.concatenate([ptrs, np.array(extra, dtype=np.uint64)])
+            self.ptrs = ptrs
+            hdr = lambda phase: rec(N.OP_ADAM_ROWS, [self.B, phase], [X["hyper"], X["ctrl"], hist_slot])      # noqa: E731
+            for h in (hdr(0), hdr(1)):
+                h["n_sub"] = len(subs)
+            pre = [hdr(0)] + subs
+            post = [hdr(1)] + subs
+            pre[0]["n_sub"] = post[0]["n_sub"] = len(subs)
+            # flush: every distinct table once
+            fsubs, seen = [], set()
+            for sub in subs:
+                key = int(ptrs[int(sub["s"][0])])
+                if key not in seen:
+                    seen.add(key)
+                    fsubs.append(sub)
+            fh = rec(N.OP_ADAM_FLUSH, [self.B, 0], [X["hyper"], X["ctrl"], hist_slot])
+            fh["n_sub"] = len(fsubs)
+            self._flush_recs = stack_ = np.stack([fh] + fsubs).astype(N.REC_DTYPE)
+            flat.flush_fn = self._flush_lazy
+        zeros = [rec(N.OP_ZERO, split(4 * gsize[a]), [self.arena_slots[a][1]]) for a in flat.size
+                 if not (lazy is not None and a == "emb")]
         adams = [rec(N.OP_ADAM, [*split(flat.size[a]), 0], [*self.arena_slots[a], X["hyper"]]) for a in flat.opt_arenas
-                 if flat.size[a] > 4 or a == "dense"]
+                 if (flat.size[a] > 4 or a == "dense") and not (lazy is not None and a == "emb")]
         stack = lambda lst: np.stack(lst).astype(N.REC_DTYPE)      # noqa: E731
-        self.recs_a = np.concatenate([prog.recs_fwd, stack([bce] + zeros), prog.recs_bwd])
-        self.recs_b = stack(adams)
+        parts = ([stack(pre)] if pre else []) + [prog.recs_fwd, stack([bce] + zeros), prog.recs_bwd]
+        self.recs_a = np.concatenate(parts)
+        self.recs_b = stack(adams + post)
         if grad_sync is None and self.exchange is None:
             self.recs_a, self.recs_b = np.concatenate([self.recs_a, self.recs_b]), None
         # typed views of the staged index columns of row-sharded fields + the gradient views the exchange routes
@@ -411,7 +524,10 @@ class FusedTrainStep:
         slot = self.k % RING
         o = slot * self.SC
         self.host_scal_np[o:o + 32].view(np.float32)[:6] = (g["lr"] / bc1, b1, b2, g["eps"], g["weight_decay"], 1.0 / math.sqrt(bc2))
-        self.host_scal_np[o + 32:o + 48].view(np.int32)[0] = slot
+        ctrl = self.host_scal_np[o + 32:o + 48].view(np.int32)
+        ctrl[0] = slot
+        if self.flat.lazy is not None:
+            ctrl[1], ctrl[2] = t, self.flat.lazy.base
         return o
 
     def step(self, x, y=None) -> LossHandle:
@@ -443,11 +559,25 @@ class FusedTrainStep:
         o = self._scalars()
         N.memcpy_async(self.dev_scal.data_ptr(), self.host_scal.data_ptr() + o, self.SC, stream)
         self._launch()
+        lz = self.flat.lazy
+        if self.lazy is not None:
+            lz.dirty = True
+            if self.flat.step % lz.flush_every == 0 or self.flat.step - lz.base + 2 >= lz.HIST_CAP:
+                self._flush_lazy()
+                if self.flat.step - lz.base + 2 >= lz.HIST_CAP:     # history table full: every row is current, start it over
+                    lz.base = self.flat.step + 1
         self.done_ev[slot].record()
         self._launched[slot] = self.k
         h = LossHandle(self, self.k)
         self.k += 1
         return h
+
+    def _flush_lazy(self):
+        """Replay every postponed row update up to the current step (device work on the current stream)."""
+        lz = self.flat.lazy
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        N.program_run(self._flush_recs, self.ptrs, stream)
+        lz.dirty = False
 
     def _read_loss(self, k: int) -> float:
         slot = k % RING

@@ -165,3 +165,109 @@ def test_packed_batches_device_and_host():
         tol = dict(atol=2 * 1e-3 * 6, rtol=0) if k in noisy else dict(atol=2e-6, rtol=1e-4)
         torch.testing.assert_close(res[0][k].float(), res[1][k].float(), **tol)
         torch.testing.assert_close(res[0][k].float(), res[2][k].float(), **tol)
+
+
+def _rec(kind, ints=(), slots=(), n_sub=0):
+    import numpy as np
+    from scenario_wise_rec_b200 import _native as N
+    r = np.zeros((), dtype=N.REC_DTYPE)
+    r["kind"], r["n_sub"] = kind, n_sub
+    r["s"][:] = -1
+    for i, v in enumerate(ints):
+        r["i"][i] = v
+    for i, v in enumerate(slots):
+        r["s"][i] = v
+    return r
+
+
+@pytest.mark.parametrize("flush_every", [1, 4, 1000])
+def test_lazy_adam_replay_is_bit_exact(flush_every):
+    """The row-lazy Adam ops (catch-up, update, flush) against the dense Adam sweep on IDENTICAL gradients: parameters and
+    both moments must be bit-identical at every checkpoint (torch.equal).  Indices are unique inside a batch so the dense
+    gradient is order-independent; most rows sit out many steps (long replays); duplicates are covered by a second
+    column that repeats the first."""
+    import math
+    import numpy as np
+    from scenario_wise_rec_b200 import _native as N
+    V, E, B, steps = 3000, 16, 64, 40
+    dev = torch.device(DEV)
+    gen = torch.Generator().manual_seed(9)
+    p0 = torch.randn(V, E, generator=gen) * 0.1
+    arrs = {}
+    for mode in ("dense", "lazy"):
+        arrs[mode] = dict(p=p0.clone().to(dev), g=torch.zeros(V, E, device=dev), m=torch.zeros(V, E, device=dev), v=torch.zeros(V, E, device=dev))
+    last = torch.zeros(V, dtype=torch.int32, device=dev)
+    claim = torch.zeros(V, dtype=torch.int32, device=dev)
+    hist = torch.zeros(4 * 4096, device=dev)
+    scal = torch.zeros(12, dtype=torch.float32, device=dev)          # 8 floats hyper + 4 ints ctrl
+    idx = torch.zeros(B, dtype=torch.int64, device=dev)
+    idx2 = torch.zeros(B, dtype=torch.int64, device=dev)
+    d, l = arrs["dense"], arrs["lazy"]
+    slots = np.array([d["p"].data_ptr(), d["g"].data_ptr(), d["m"].data_ptr(), d["v"].data_ptr(), scal.data_ptr(), scal.data_ptr() + 32,
+                      l["p"].data_ptr(), l["g"].data_ptr(), l["m"].data_ptr(), l["v"].data_ptr(), last.data_ptr(), claim.data_ptr(),
+                      idx.data_ptr(), hist.data_ptr(), idx2.data_ptr()], dtype=np.uint64)
+    n = V * E
+    dense = np.stack([_rec(N.OP_ADAM, [n, 0, 1], [0, 1, 2, 3, 4])]).astype(N.REC_DTYPE)       # zero_grad = 1
+    sub = lambda s: _rec(N.OP_GROUP, [V, 0, N.DT_I64, 0, 0, E], [6, 7, 8, 9, 10, 11, s])      # noqa: E731
+    rows = lambda phase: np.stack([_rec(N.OP_ADAM_ROWS, [B, phase], [4, 5, 13], n_sub=2), sub(12), sub(14)]).astype(N.REC_DTYPE)   # noqa: E731
+    flush = np.stack([_rec(N.OP_ADAM_FLUSH, [B, 0], [4, 5, 13], n_sub=1), sub(12)]).astype(N.REC_DTYPE)
+    st = torch.cuda.current_stream().cuda_stream
+    lr, b1, b2, eps, wd = 1e-2, 0.9, 0.999, 1e-8, 1e-3
+    for t in range(1, steps + 1):
+        bc1, bc2 = 1 - b1 ** t, 1 - b2 ** t
+        h = torch.tensor([lr / bc1, b1, b2, eps, wd, 1 / math.sqrt(bc2), 0, 0], dtype=torch.float32)
+        c = torch.tensor([0, t, 1, 0], dtype=torch.int32)
+        scal.copy_(torch.cat([h, c.view(torch.float32)]))
+        rows_t = torch.randperm(V, generator=gen)[:B]
+        idx.copy_(rows_t)
+        idx2.copy_(rows_t.flip(0))                                   # every row is looked up twice per batch
+        grad = (torch.randn(B, E, generator=gen) * 0.05).to(dev)
+        N.program_run(rows(0), slots, st)                            # catch-up before the rows would be read
+        d["g"][rows_t.to(dev)] = grad
+        l["g"][rows_t.to(dev)] = grad
+        N.program_run(dense, slots, st)
+        N.program_run(rows(1), slots, st)
+        if t % flush_every == 0 or t == steps:
+            N.program_run(flush, slots, st)
+            torch.cuda.synchronize()
+            for k in ("p", "m", "v"):
+                assert torch.equal(d[k], l[k]), (k, t)
+            assert float(l["g"].abs().max()) == 0.0                  # consumed gradient rows are zeroed again
+            assert int(last.min()) == t
+
+
+def test_lazy_adam_matches_the_dense_trajectory(monkeypatch):
+    """End to end: the fused trainer with row-lazy Adam against the same trainer sweeping every row densely
+    (SWR_LAZY_ADAM=0), whatever the flush interval.  Two runs of the same trainer already differ by the rounding of atomic
+    gradient sums (which Adam's normalisation amplifies), so the comparison uses the tolerance of the other trajectory
+    tests; bit-exactness of the replay itself is test_lazy_adam_replay_is_bit_exact."""
+    import workloads
+    feats = [("a", "sparse", 5000, 16), ("b", "sparse", 37, 16), ("c", "sparse", 900, 16), ("d0", "dense", 0, 1)]
+    cfg = dict(features=feats, domain_num=3, n_expert=2, expert_dims=[32, 16], tower_dims=[8])
+    B, steps = 64, 23
+    batches = [workloads.make_batch(feats, B, 3, seed=50 + i) for i in range(steps)]
+    results = []
+    for mode, flush in (("0", "32"), ("1", "5"), ("1", "1000")):
+        monkeypatch.setenv("SWR_LAZY_ADAM", mode)
+        monkeypatch.setenv("SWR_LAZY_FLUSH", flush)
+        torch.manual_seed(3)
+        m = model_factory.build("MMOE", cfg)
+        t = CTRTrainer(m, "lazy", optimizer_params={"lr": 1e-2, "weight_decay": 1e-3}, device=DEV)
+        m.train()
+        for x, y in batches:
+            t.train_step(x, y)
+        assert (t._flat.lazy is not None) == (mode == "1")
+        sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+        od = t.optimizer.state_dict()["state"]
+        results.append((sd, {k: {n: (v.cpu().clone() if torch.is_tensor(v) else v) for n, v in st.items()} for k, st in od.items()}))
+    (sd0, od0) = results[0]
+    names = [k for k, _ in m.named_parameters()]
+    for sd, od in results[1:]:
+        for k in sd0:
+            if "embed_dict" in k:
+                torch.testing.assert_close(sd[k], sd0[k], atol=2e-5, rtol=2e-4, msg=lambda s_, k=k: f"{k}: {s_}")
+        for pid, st in od0.items():
+            if "embed_dict" in names[pid]:
+                torch.testing.assert_close(od[pid]["exp_avg"], st["exp_avg"], atol=1e-6, rtol=2e-3)
+                torch.testing.assert_close(od[pid]["exp_avg_sq"], st["exp_avg_sq"], atol=1e-9, rtol=2e-3)
+                assert float(od[pid]["step"]) == float(st["step"]) == steps
