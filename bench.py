@@ -384,7 +384,7 @@ def main():
     model_name, cfg, B = workloads.CASES[args.workload]
     feats = workloads.all_feature_specs(cfg)
     torch.manual_seed(0)                     # identical initial weights on every rank
-    model = model_factory.build(model_name, cfg)
+    model = model_factory.build(model_name, cfg, shard_min_rows=args.shard_min_rows if world > 1 else 0)
     trainer = CTRTrainer(model, "synthetic", optimizer_params={"lr": 1e-3, "weight_decay": 1e-5}, device=str(dev))
     if world > 1:
         trainer.enable_data_parallel()

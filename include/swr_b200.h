@@ -185,6 +185,19 @@ SWR_API int swr_program_run(const swr_rec_t* recs, int32_t n_recs, void* const* 
  * packed batch (pinned host staging -> device staging) and the D2H read-back of the loss ring. */
 SWR_API int swr_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Peer memory for row-sharded embedding tables (one process per GPU on one NVSwitch node; no reference counterpart:
+ * the reference keeps every table whole on one device, basic/features.py:76-79).  A rank allocates its shard arenas
+ * with swr_peer_alloc, publishes the 64-byte handle (torch.distributed all_gather), and maps every peer's arena with
+ * swr_peer_open; K1 then reads looked-up rows and K2 adds gradient rows directly in the owner's memory over NVLink.
+ * ---------------------------------------------------------------------------------- */
+#define SWR_PEER_HANDLE_BYTES 64
+SWR_API int swr_peer_alloc(int64_t bytes, void** ptr);                 /* cudaMalloc + zero fill                   */
+SWR_API int swr_peer_free(void* ptr);
+SWR_API int swr_peer_handle(void* ptr, unsigned char* handle64);       /* cudaIpcGetMemHandle                      */
+SWR_API int swr_peer_open(const unsigned char* handle64, void** ptr);  /* cudaIpcOpenMemHandle (lazy peer access)  */
+SWR_API int swr_peer_close(void* ptr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -141,13 +141,15 @@ static int run_lazy_adam(const swr_rec_t& h, const swr_rec_t* subs, bool flush, 
 
 static int run_gather(const swr_rec_t& h, const swr_rec_t* subs, Ctx& c, cudaStream_t st) {
   const int n = h.n_sub;
-  std::vector<const float*> tables; std::vector<int64_t> vocab; std::vector<const void*> idx; std::vector<int32_t> idt, E;
+  std::vector<const float*> tables; std::vector<int64_t> vocab; std::vector<const void*> idx; std::vector<int32_t> idt, E, world;
+  std::vector<const float* const*> peers;
   std::vector<const void*> dense; std::vector<int32_t> ddt;
   for (int i = 0; i < n; ++i) {
     const swr_rec_t& r = subs[i];
     if (r.i[4] == 0) {
       tables.push_back(static_cast<const float*>(c.slot(r.s[0]))); idx.push_back(c.slot(r.s[1]));
       vocab.push_back(((int64_t)(uint32_t)r.i[0]) | ((int64_t)r.i[1] << 32)); idt.push_back(r.i[2]); E.push_back(r.i[5]);
+      world.push_back(r.i[6]); peers.push_back(static_cast<const float* const*>(c.slot(r.s[2])));
     } else {
       dense.push_back(c.slot(r.s[0])); ddt.push_back(r.i[2]);
     }
@@ -156,20 +158,24 @@ static int run_gather(const swr_rec_t& h, const swr_rec_t* subs, Ctx& c, cudaStr
   GatherLaunch g{tables.data(), vocab.data(), idx.data(), idt.data(), E.data(), dense.data(), ddt.data(),
                  static_cast<float*>(c.slot(h.s[0])) + h.i[5], h.i[4], h.i[0], (int)tables.size(), (int)dense.size(),
                  static_cast<int32_t*>(c.slot(h.s[1]))};
+  g.world = world.data(); g.peers = peers.data();
   return launch_gather(g, st);
 }
 
 static int run_scatter(const swr_rec_t& h, const swr_rec_t* subs, Ctx& c, cudaStream_t st) {
   const int n = h.n_sub;
-  std::vector<float*> gt(n); std::vector<int64_t> vocab(n); std::vector<const void*> idx(n); std::vector<int32_t> idt(n), E(n), col(n);
+  std::vector<float*> gt(n); std::vector<int64_t> vocab(n); std::vector<const void*> idx(n); std::vector<int32_t> idt(n), E(n), col(n), world(n);
+  std::vector<float* const*> peers(n);
   for (int i = 0; i < n; ++i) {
     const swr_rec_t& r = subs[i];
     gt[i] = static_cast<float*>(c.slot(r.s[0])); idx[i] = c.slot(r.s[1]);
     vocab[i] = ((int64_t)(uint32_t)r.i[0]) | ((int64_t)r.i[1] << 32); idt[i] = r.i[2]; col[i] = r.i[3]; E[i] = r.i[5];
+    world[i] = r.i[6]; peers[i] = static_cast<float* const*>(c.slot(r.s[2]));
   }
   if (!c.ok) return SWR_ERR_INVALID;
   ScatterLaunch s{static_cast<const float*>(c.slot(h.s[0])), h.i[4], h.i[0], idx.data(), idt.data(), gt.data(), vocab.data(),
                   E.data(), col.data(), n};
+  s.world = world.data(); s.peers = peers.data();
   return launch_scatter(s, st);
 }
 
@@ -437,6 +443,33 @@ SWR_API int swr_memcpy_async(void* dst, const void* src, int64_t bytes, void* st
   SWR_CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
   return SWR_OK;
 }
+
+SWR_API int swr_peer_alloc(int64_t bytes, void** ptr) {
+  g_err[0] = 0;
+  if (bytes <= 0 || !ptr) { set_error("peer_alloc: bad argument"); return SWR_ERR_INVALID; }
+  SWR_CUDA_OK(cudaMalloc(ptr, (size_t)bytes));
+  SWR_CUDA_OK(cudaMemset(*ptr, 0, (size_t)bytes));
+  return SWR_OK;
+}
+SWR_API int swr_peer_free(void* ptr) { g_err[0] = 0; if (ptr) SWR_CUDA_OK(cudaFree(ptr)); return SWR_OK; }
+SWR_API int swr_peer_handle(void* ptr, unsigned char* handle64) {
+  g_err[0] = 0;
+  static_assert(sizeof(cudaIpcMemHandle_t) == SWR_PEER_HANDLE_BYTES, "handle size");
+  if (!ptr || !handle64) { set_error("peer_handle: bad argument"); return SWR_ERR_INVALID; }
+  cudaIpcMemHandle_t h;
+  SWR_CUDA_OK(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle64, &h, sizeof(h));
+  return SWR_OK;
+}
+SWR_API int swr_peer_open(const unsigned char* handle64, void** ptr) {
+  g_err[0] = 0;
+  if (!ptr || !handle64) { set_error("peer_open: bad argument"); return SWR_ERR_INVALID; }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  SWR_CUDA_OK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return SWR_OK;
+}
+SWR_API int swr_peer_close(void* ptr) { g_err[0] = 0; if (ptr) SWR_CUDA_OK(cudaIpcCloseMemHandle(ptr)); return SWR_OK; }
 
 SWR_API int swr_profile_begin(void) {
   std::lock_guard<std::mutex> lk(g_prof_mu);

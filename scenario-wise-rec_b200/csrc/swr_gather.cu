@@ -20,7 +20,8 @@ struct SparseField {
   int dtype;
   int E;
   int col;              // first output column of this field
-  int pad;
+  int world;            // > 0: the table is row-sharded over `world` ranks: row r lives on rank r % world at local row r / world,
+  float* const* peers;  //      peers[rank] = base of that rank's shard (K1: weights, K2: gradient); reached over NVLink
 };
 struct DenseField { const void* ptr; int dtype; int col; };
 
@@ -63,8 +64,14 @@ __device__ __forceinline__ void stage_offsets(const P& p, int64_t b0, int nb, in
     int64_t off = -1;
     if (bl < nb) {
       const int64_t ix = load_index(p.sp[f].idx, p.sp[f].dtype, b0 + bl);
-      if (ix >= 0 && ix < p.sp[f].vocab) off = ix * p.sp[f].E;
-      else if (oob) { oob[0] = 1; oob[1] = f; }
+      if (ix >= 0 && ix < p.sp[f].vocab) {
+        if (p.sp[f].world > 0) {      // absolute address (in floats) of the row in its owner's shard
+          const int w = p.sp[f].world;
+          off = (int64_t)(reinterpret_cast<uintptr_t>(p.sp[f].peers[ix % w]) >> 2) + (ix / w) * p.sp[f].E;
+        } else {
+          off = ix * p.sp[f].E;
+        }
+      } else if (oob) { oob[0] = 1; oob[1] = f; }
     }
     rowoff[i] = off;
   }
@@ -96,7 +103,7 @@ __global__ void __launch_bounds__(256) gather_vec_kernel(const __grid_constant__
     const int f = cmap[c4] >> 8, q = cmap[c4] & 0xff;
     const int64_t off = rowoff[f * TB + bl];
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (off >= 0) v = ldg_stream(reinterpret_cast<const float4*>(p.sp[f].table + off) + q);
+    if (off >= 0) v = ldg_stream(reinterpret_cast<const float4*>((p.sp[f].world > 0 ? static_cast<const float*>(nullptr) : p.sp[f].table) + off) + q);
     *reinterpret_cast<float4*>(p.out + (b0 + bl) * p.ld + 4 * c4) = v;
   }
   // dense scalars: thread -> (j, bl) with bl fastest so the column reads coalesce
@@ -126,7 +133,7 @@ __global__ void __launch_bounds__(256) gather_scalar_kernel(const __grid_constan
     const int bl = i / p.S, c = i - bl * p.S;
     const int f = cfield[c];
     const int64_t off = rowoff[f * TB + bl];
-    p.out[(b0 + bl) * p.ld + c] = off >= 0 ? __ldg(p.sp[f].table + off + (c - p.sp[f].col)) : 0.f;
+    p.out[(b0 + bl) * p.ld + c] = off >= 0 ? __ldg((p.sp[f].world > 0 ? static_cast<const float*>(nullptr) : p.sp[f].table) + off + (c - p.sp[f].col)) : 0.f;
   }
   for (int i = threadIdx.x; i < p.n_dense * nb; i += blockDim.x) {
     const int j = i / nb, bl = i - j * nb;
@@ -160,7 +167,8 @@ __global__ void __launch_bounds__(256) scatter_kernel(const __grid_constant__ Sc
     const SparseField& sf = p.sp[f];
     const int E = sf.E;
     const int64_t tbl = sf.vocab * E;
-    if (tbl <= kPrivFloats) {
+    float* const gbase = sf.world > 0 ? static_cast<float*>(nullptr) : sf.gtable;   // sharded: rowoff holds absolute addresses
+    if (tbl <= kPrivFloats && sf.world == 0) {
       for (int i = threadIdx.x; i < (int)tbl; i += blockDim.x) priv[i] = 0.f;
       __syncthreads();
       for (int i = threadIdx.x; i < nb * E; i += blockDim.x) {
@@ -204,18 +212,18 @@ __global__ void __launch_bounds__(256) scatter_kernel(const __grid_constant__ Sc
               const float4 o = stage[(threadIdx.x & ~31) + src];
               v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
             }
-            red_add_v4(sf.gtable + dst, v);
+            red_add_v4(gbase + dst, v);
           }
           __syncwarp();
         } else if (dst >= 0) {
-          red_add_v4(sf.gtable + dst, v);
+          red_add_v4(gbase + dst, v);
         }
       }
     } else {
       for (int i = threadIdx.x; i < nb * E; i += blockDim.x) {
         const int bl = i / E, e = i - bl * E;
         const int64_t off = rowoff[f * TB + bl];
-        if (off >= 0) atomicAdd(sf.gtable + off + e, p.g[(b0 + bl) * p.ld + sf.col + e]);
+        if (off >= 0) atomicAdd(gbase + off + e, p.g[(b0 + bl) * p.ld + sf.col + e]);
       }
     }
   }
@@ -259,8 +267,10 @@ int launch_gather(const GatherLaunch& g, cudaStream_t st) {
   for (int f = 0; f < g.n_sparse; ++f) {
     p.sp[f].table = g.tables[f]; p.sp[f].gtable = nullptr; p.sp[f].idx = g.idx[f]; p.sp[f].vocab = g.vocab[f];
     p.sp[f].dtype = g.idx_dtype[f]; p.sp[f].E = g.E[f]; p.sp[f].col = col;
+    p.sp[f].world = g.world ? g.world[f] : 0; p.sp[f].peers = g.peers ? const_cast<float* const*>(g.peers[f]) : nullptr;
+    if (p.sp[f].world > 0 && !p.sp[f].peers) { set_error("gather: sharded field %d without peer table", f); return SWR_ERR_INVALID; }
     if (g.E[f] <= 0 || g.E[f] > 1020) { set_error("gather: embed_dim %d unsupported", g.E[f]); return SWR_ERR_UNSUPPORTED; }
-    vec = vec && (g.E[f] % 4 == 0) && aligned16(g.tables[f]);
+    vec = vec && (g.E[f] % 4 == 0) && (p.sp[f].world > 0 || aligned16(g.tables[f]));
     col += g.E[f];
   }
   p.S = col; p.S4 = col / 4;
@@ -290,6 +300,8 @@ int launch_scatter(const ScatterLaunch& s, cudaStream_t st) {
   for (int f = 0; f < s.n_sparse; ++f) {
     p.sp[f].table = nullptr; p.sp[f].gtable = s.gtables[f]; p.sp[f].idx = s.idx[f]; p.sp[f].vocab = s.vocab[f];
     p.sp[f].dtype = s.idx_dtype[f]; p.sp[f].E = s.E[f]; p.sp[f].col = s.col ? s.col[f] : col;
+    p.sp[f].world = s.world ? s.world[f] : 0; p.sp[f].peers = s.peers ? s.peers[f] : nullptr;
+    if (p.sp[f].world > 0 && !p.sp[f].peers) { set_error("scatter: sharded field %d without peer table", f); return SWR_ERR_INVALID; }
     col += s.E[f];
   }
   p.g = s.g; p.ld = s.ld; p.B = s.B; p.n_sparse = s.n_sparse;

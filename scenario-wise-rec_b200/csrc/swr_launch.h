@@ -12,6 +12,8 @@ struct GatherLaunch {
   const int32_t* E;                 // per-field embed dim
   const void* const* dense; const int32_t* dense_dtype;
   float* out; int64_t ld; int64_t B; int n_sparse; int n_dense; int32_t* oob;
+  const int32_t* world = nullptr;                 // per field: > 0 = row-sharded over that many ranks (vocab = full vocabulary)
+  const float* const* const* peers = nullptr;     // per field: device array of `world` shard base pointers
 };
 int launch_gather(const GatherLaunch& g, cudaStream_t st);
 
@@ -20,6 +22,8 @@ struct ScatterLaunch {
   const void* const* idx; const int32_t* idx_dtype; float* const* gtables; const int64_t* vocab;
   const int32_t* E; const int32_t* col;   // col may be null (fields packed in order)
   int n_sparse;
+  const int32_t* world = nullptr;          // per field: > 0 = row-sharded gradient (see GatherLaunch)
+  float* const* const* peers = nullptr;
 };
 int launch_scatter(const ScatterLaunch& s, cudaStream_t st);
 

@@ -40,7 +40,8 @@ FC_SIMT, FC_TC, FC_AUTO = 0, 1, 2   # swr_fc_mode
 
 EXPORTS = ("swr_abi_version", "swr_last_error", "swr_launch_count", "swr_device_check", "swr_set_fc_mode", "swr_get_fc_mode",
            "swr_profile_begin", "swr_profile_end", "swr_memcpy_async",
-           "swr_embedding_gather_fwd", "swr_embedding_scatter_bwd", "swr_program_run")
+           "swr_embedding_gather_fwd", "swr_embedding_scatter_bwd", "swr_program_run",
+           "swr_peer_alloc", "swr_peer_free", "swr_peer_handle", "swr_peer_open", "swr_peer_close")
 
 _lib = None
 
@@ -74,6 +75,13 @@ def lib():
     L.swr_profile_begin.restype = ctypes.c_int
     L.swr_profile_end.restype = ctypes.c_int
     L.swr_profile_end.argtypes = [vp, vp, vp, i32]
+    for fn in (L.swr_peer_alloc, L.swr_peer_free, L.swr_peer_handle, L.swr_peer_open, L.swr_peer_close):
+        fn.restype = ctypes.c_int
+    L.swr_peer_alloc.argtypes = [i64, vp]
+    L.swr_peer_free.argtypes = [vp]
+    L.swr_peer_handle.argtypes = [vp, vp]
+    L.swr_peer_open.argtypes = [vp, vp]
+    L.swr_peer_close.argtypes = [vp]
     if L.swr_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libswr_b200.so ABI {L.swr_abi_version()} != expected {ABI_VERSION}; rebuild")
     _lib = L

@@ -84,7 +84,9 @@ class EmbeddingLayer(FusedModule):
         feas = [f for f in features if isinstance(f, SparseFeature)]
         out = []
         for (name, tab), fea in zip(sparse, feas):
-            if getattr(fea, "shard", None) is not None:
+            if getattr(fea, "shard", None) is not None and b.p2p:
+                out.append((name, b.peer_table(fea, tab)))      # K1 / K2 address the owners' shards directly (NVLink)
+            elif getattr(fea, "shard", None) is not None:
                 f = b.virtual_field(fea, tab)
                 col_dtypes[f.vcol] = torch.int64
                 out.append((f.vcol, f.virt))

@@ -102,6 +102,61 @@ def load_full_state_dict(model, state: Dict[str, torch.Tensor], strict: bool = T
     return model.load_state_dict(state, strict=strict)
 
 
+# ---- peer memory: shard arenas every rank of the node can address (NVLink / NVSwitch) -------------------------------
+class PeerArena:
+    """A float32 device buffer of ``numel`` elements allocated outside torch's caching allocator (swr_peer_alloc) whose
+    CUDA IPC handle is exchanged over ``group``: ``ptrs[r]`` is the address of rank r's buffer in THIS process (own
+    rank: the local pointer).  ``tensor`` views the local buffer.  Same size on every rank."""
+
+    def __init__(self, numel: int, device: torch.device, group=None):
+        L = N.lib()
+        self.numel, self.device, self.group = int(numel), device, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        ptr = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            N.check(L.swr_peer_alloc(4 * self.numel, ctypes.byref(ptr)), "swr_peer_alloc")
+            handle = (ctypes.c_ubyte * 64)()
+            N.check(L.swr_peer_handle(ptr, handle), "swr_peer_handle")
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+            allh = torch.empty(self.world, 64, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(allh.view(-1), mine, group=group)
+            allh = allh.cpu()
+            self.local_ptr = int(ptr.value)
+            self.ptrs = []
+            for r in range(self.world):
+                if r == self.rank:
+                    self.ptrs.append(self.local_ptr)
+                    continue
+                buf = (ctypes.c_ubyte * 64)(*allh[r].tolist())
+                q = ctypes.c_void_p()
+                N.check(L.swr_peer_open(buf, ctypes.byref(q)), "swr_peer_open")
+                self.ptrs.append(int(q.value))
+        self.tensor = torch.as_tensor(_CudaArray(self.local_ptr, self.numel, self), device=device)
+        dist.barrier(group=group)
+
+    def peer_table(self, offset: int) -> torch.Tensor:
+        """Device int64 [world]: address of element ``offset`` of every rank's buffer (kernel argument of K1 / K2)."""
+        return torch.tensor([q + 4 * int(offset) for q in self.ptrs], dtype=torch.int64, device=self.device)
+
+    def __del__(self):
+        try:
+            L = N.lib()
+            for r, q in enumerate(self.ptrs):
+                if r != self.rank:
+                    L.swr_peer_close(ctypes.c_void_p(q))
+            L.swr_peer_free(ctypes.c_void_p(self.local_ptr))
+        except Exception:
+            pass
+
+
+class _CudaArray:
+    """__cuda_array_interface__ view of a raw device allocation (keeps its owner alive)."""
+
+    def __init__(self, ptr: int, numel: int, owner):
+        self._owner = owner
+        self.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+
+
 # ---- local row gather / scatter through the C ABI (K1 / K2 on one field) ---------------------------------
 def local_gather(table: torch.Tensor, idx: torch.Tensor, out: torch.Tensor):
     """out[i] = table[idx[i]] (zero row when idx[i] is outside [0, rows)); no out-of-range flag."""

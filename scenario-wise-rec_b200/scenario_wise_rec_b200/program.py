@@ -119,8 +119,10 @@ class ProgramBuilder:
         self.params: List[torch.nn.Parameter] = []
         self._param_slot: Dict[int, int] = {}
         self.param_arena: List[Tuple[str, int, int]] = []
-        self.arena_size = {"dense": 0, "emb": 0, "virt": 0}
+        self.arena_size = {"dense": 0, "emb": 0, "virt": 0, "shard": 0}
         self.exchange = None                 # parallel.ShardedExchange of the owning model (row-sharded tables)
+        self.p2p = False                     # row-sharded tables are read / updated in their owners' memory (peer pointers)
+        self.peer_tabs: Dict[int, tuple] = {}  # id(shard parameter) -> (parameter, full vocabulary, world)
         self.virtual_fields: list = []
         self.tape: List[tuple] = []
         self.norm_acts: List[Act] = []
@@ -170,6 +172,12 @@ class ProgramBuilder:
             self._param_slot[key] = self._new_slot(("grad", arena, off, p.numel()))
         return self._param_slot[key]
 
+    def _peer_slot(self, kind: str, tab) -> int:
+        key = (kind, id(tab))
+        if key not in self._static:
+            self._static[key] = self._new_slot(("special", (kind, tab)))
+        return self._static[key]
+
     def virtual_field(self, fea, shard_param):
         """The virtual table of a row-sharded feature for this batch size (see parallel.py)."""
         if self.exchange is None:
@@ -178,6 +186,11 @@ class ProgramBuilder:
         if f not in self.virtual_fields:
             self.virtual_fields.append(f)
         return f
+
+    def peer_table(self, fea, shard_param):
+        """Register a row-sharded table that the gather reads (and the scatter updates) through peer pointers."""
+        self.peer_tabs[id(shard_param)] = (shard_param, int(fea.vocab_size), int(fea.shard.world))
+        return shard_param
 
     # ---- activations ------------------------------------------------------------------
     def new_act(self, n: int, norm: Optional[Norm] = None, act: int = N.ACT_NONE, raw: Optional[int] = None,
@@ -554,13 +567,20 @@ class ProgramBuilder:
                         r = self._rec(N.OP_GROUP)
                         vocab, E = int(tab.shape[0]), int(tab.shape[1])
                         r["s"][0], r["s"][1] = self.static(tab), self.input(name)
+                        peer = self.peer_tabs.get(id(tab))
+                        if peer is not None:      # vocabulary = the whole table; rows live at peers[row % world]
+                            vocab = peer[1]
+                            r["i"][6] = peer[2]
+                            r["s"][2] = self._peer_slot("peers_p", tab)
                         r["i"][0], r["i"][1] = self._split64(vocab)
                         r["i"][2], r["i"][3], r["i"][4], r["i"][5] = N.torch_dtype_code(dts[name]), col, 0, E
                         subs.append(r)
                         if tab.requires_grad and diff:
                             g = r.copy()
                             is_virt = any(tab is f.virt for f in self.virtual_fields)
-                            g["s"][0] = self.grad(tab, "virt" if is_virt else "emb")
+                            g["s"][0] = self.grad(tab, "virt" if is_virt else ("shard" if peer is not None else "emb"))
+                            if peer is not None:
+                                g["s"][2] = self._peer_slot("peers_g", tab)
                             srecs.append(g)
                         col += E
                     for name in dense:

@@ -57,7 +57,8 @@ class FlatArenas:
         self.device = device
         entries = [(p, a, off, n) for p, (a, off, n) in zip(prog.params, prog.param_arena)]
         self.size = {k: max(v, 4) for k, v in prog.arena_size.items()}
-        off = 0
+        # shards of the NCCL-exchange path (virtual tables) follow the shard tables the program itself addresses (peer path)
+        off = prog.arena_size.get("shard", 0)
         self.shards = []
         for f in prog.virtual_fields:
             if f.shard.requires_grad and all(f.shard is not q for q, *_ in self.shards):
@@ -66,9 +67,24 @@ class FlatArenas:
         self.size["shard"] = max(off, 4)
         self.layout = [(id(p), a, o, n) for p, a, o, n in entries]
         z = lambda k: torch.zeros(self.size[k], dtype=torch.float32, device=device)      # noqa: E731
-        self.g = {k: z(k) for k in self.size}
+        # dense + emb gradients are contiguous: data-parallel replicas sum them with ONE all-reduce
+        self.g_repl = torch.zeros(self.size["dense"] + self.size["emb"], dtype=torch.float32, device=device)
+        self.g = {k: z(k) for k in self.size if k not in ("dense", "emb")}
+        self.g["dense"] = self.g_repl[:self.size["dense"]]
+        self.g["emb"] = self.g_repl[self.size["dense"]:]
         self.opt_arenas = [k for k in self.size if k != "virt"]
         self.p = {k: z(k) for k in self.opt_arenas}
+        # peer path: the shard parameters and their gradients live in memory every rank of the node can address
+        self.peer = None
+        self.peer_tables = {}
+        if prog.arena_size.get("shard", 0) > 0:
+            from ..parallel import PeerArena
+            self.peer = {"p": PeerArena(self.size["shard"], device), "g": PeerArena(self.size["shard"], device)}
+            self.p["shard"], self.g["shard"] = self.peer["p"].tensor, self.peer["g"].tensor
+            for p_, a, o, n in entries:
+                if a == "shard":
+                    self.peer_tables[("peers_p", id(p_))] = self.peer["p"].peer_table(o)
+                    self.peer_tables[("peers_g", id(p_))] = self.peer["g"].peer_table(o)
         self.m = {k: z(k) for k in self.opt_arenas}
         self.v = {k: z(k) for k in self.opt_arenas}
         self.params = []
@@ -210,6 +226,10 @@ class FusedTrainStep:
         self.key = (self.B, tuple(self.dts.values()))
         b = ProgramBuilder(self.B, True)
         b.exchange = model._get_exchange()
+        import torch.distributed as dist
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        # row-sharded tables: K1 / K2 address the owners' shards over NVLink peer pointers (SWR_SHARD_P2P=0: NCCL exchange)
+        b.p2p = bool(multi and b.exchange is not None and os.environ.get("SWR_SHARD_P2P", "1") != "0")
         model._lower(b, dict(self.dts))
         prog = b.finish()
         self.exchange = b.exchange if prog.virtual_fields else None
@@ -289,6 +309,8 @@ class FusedTrainStep:
         for i, d in enumerate(prog.slot_desc):
             if d[0] == "grad":
                 ptrs[i] = self.g[d[1]].data_ptr() + 4 * d[2]
+            elif d[0] == "special" and isinstance(d[1], tuple):      # device table of every rank's shard address
+                ptrs[i] = flat.peer_tables[(d[1][0], id(d[1][1]))].data_ptr()
         ptrs[X["label"]] = base + self.y_off
         ptrs[X["loss"]] = self.loss_ring_dev.data_ptr()
         ptrs[X["hyper"]] = self.dev_scal.data_ptr()
@@ -315,8 +337,14 @@ class FusedTrainStep:
         split = ProgramBuilder._split64
         # Data-parallel table gradients as rows instead of a dense all-reduce (see _setup_sparse_sync): every rank then
         # scales its loss gradient by 1 / world, so that cross-rank *sums* are the global-batch mean.
-        self.sparse_sync = self._setup_sparse_sync(prog, ptrs)
+        self.p2p = flat.peer is not None
+        self.sparse_sync = None if self.p2p else self._setup_sparse_sync(prog, ptrs)
         gscale = 1.0 / self.sparse_sync["world"] if self.sparse_sync else 1.0
+        if self.p2p:
+            # every rank's loss gradient is scaled by 1 / world: the rows added into the owners' shards and the summed
+            # replicated gradients are then those of the global-batch mean
+            gscale = 1.0 / dist.get_world_size()
+            self._bar = torch.zeros(1, dtype=torch.float32, device=device)
         bce = rec(N.OP_BCE, [self.B, N.DT_F32, RING], [prog.out_slot, X["label"], prog.gout_slot, X["loss"], X["ctrl"]], [gscale])
         lazy = flat.lazy if (grad_sync is None and self.exchange is None) else None
         self.lazy = lazy
@@ -372,15 +400,17 @@ class FusedTrainStep:
             fh["n_sub"] = len(fsubs)
             self._flush_recs = stack_ = np.stack([fh] + fsubs).astype(N.REC_DTYPE)
             flat.flush_fn = self._flush_lazy
+        # peer mode: a shard's gradient is written by every rank, so it is zeroed by its own Adam sweep (zero_grad flag)
+        # at the end of the step, before the barrier that opens the next one -- not in the middle of this one
         zeros = [rec(N.OP_ZERO, split(4 * gsize[a]), [self.arena_slots[a][1]]) for a in flat.size
-                 if not (lazy is not None and a == "emb")]
-        adams = [rec(N.OP_ADAM, [*split(flat.size[a]), 0], [*self.arena_slots[a], X["hyper"]]) for a in flat.opt_arenas
-                 if (flat.size[a] > 4 or a == "dense") and not (lazy is not None and a == "emb")]
+                 if not (lazy is not None and a == "emb") and not (self.p2p and a == "shard")]
+        adams = [rec(N.OP_ADAM, [*split(flat.size[a]), 1 if (self.p2p and a == "shard") else 0], [*self.arena_slots[a], X["hyper"]])
+                 for a in flat.opt_arenas if (flat.size[a] > 4 or a == "dense") and not (lazy is not None and a == "emb")]
         stack = lambda lst: np.stack(lst).astype(N.REC_DTYPE)      # noqa: E731
         parts = ([stack(pre)] if pre else []) + [prog.recs_fwd, stack([bce] + zeros), prog.recs_bwd]
         self.recs_a = np.concatenate(parts)
         self.recs_b = stack(adams + post)
-        if grad_sync is None and self.exchange is None:
+        if grad_sync is None and self.exchange is None and not self.p2p:
             self.recs_a, self.recs_b = np.concatenate([self.recs_a, self.recs_b]), None
         # typed views of the staged index columns of row-sharded fields + the gradient views the exchange routes
         self._vf = []
@@ -465,6 +495,11 @@ class FusedTrainStep:
     # ---- device work of one step (graph-capturable: no syncs, no allocations) ------------------------
     def _body(self):
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        import torch.distributed as dist
+        if self.p2p:
+            # every owner has finished the previous step's Adam sweep (and zeroed its shard gradient) before any rank
+            # reads or adds rows in it
+            dist.all_reduce(self._bar, op=dist.ReduceOp.SUM)
         for f, idx, _gv, _gs in self._vf:              # embedding exchange, forward half (NCCL over NVLink)
             self.exchange.lookup(f, idx)
         N.program_run(self.recs_a, self.ptrs, stream)
@@ -472,7 +507,11 @@ class FusedTrainStep:
             for f, _idx, gv, gs in self._vf:           # backward half: route virtual-table gradients to their owners
                 if gv is not None and gs is not None:
                     self.exchange.route_grad(f, gv, gs)
-            if self.sparse_sync is not None:
+            if self.p2p:
+                # ONE all-reduce sums the replicated gradients (tower / expert / gate weights + small tables); it is also the
+                # barrier behind which every rank's K2 has finished adding rows into the owners' shard gradients
+                dist.all_reduce(self.flat.g_repl, op=dist.ReduceOp.SUM)
+            elif self.sparse_sync is not None:
                 self._sparse_grad_sync(stream)
             elif self.grad_sync is not None:
                 self.grad_sync(self.flat.g)

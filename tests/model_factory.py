@@ -5,13 +5,18 @@ from scenario_wise_rec_b200.basic.features import DenseFeature, SparseFeature
 import scenario_wise_rec_b200.models.multi_domain as M
 
 
-def features(spec):
-    """Fresh feature objects (they cache their nn.Embedding)."""
-    return [SparseFeature(n, vocab_size=v, embed_dim=d) if k == "sparse" else DenseFeature(n) for n, k, v, d in spec]
+def features(spec, shard_min_rows=0):
+    """Fresh feature objects (they cache their nn.Embedding).  shard_min_rows > 0 (one process per GPU): tables with at
+    least that many rows are row-sharded over the default process group (parallel.shard_features)."""
+    feats = [SparseFeature(n, vocab_size=v, embed_dim=d) if k == "sparse" else DenseFeature(n) for n, k, v, d in spec]
+    if shard_min_rows > 0:
+        from scenario_wise_rec_b200 import parallel
+        parallel.shard_features(feats, min_rows=shard_min_rows)
+    return feats
 
 
-def build(model_name, cfg):
-    f = lambda key: features(cfg[key])   # noqa: E731
+def build(model_name, cfg, shard_min_rows=0):
+    f = lambda key: features(cfg[key], shard_min_rows)   # noqa: E731
     D = cfg.get("domain_num")
     if model_name == "SharedBottom":
         return M.SharedBottom(f("features"), D, bottom_params={"dims": list(cfg["bottom_dims"])},
