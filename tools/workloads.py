@@ -13,13 +13,15 @@ ALI_VOCAB = [238635, 98, 14, 3, 8, 4, 4, 3, 5, 467298, 6929, 263942, 80232, 1063
              3, 5853, 105622, 53843, 31858]
 
 
-def ali_ccp_features(scale=1, embed_dim=16):
+def ali_ccp_features(scale=1, embed_dim=16, item_rows=None):
+    """item_rows: size of the item table (field s9); BASELINE.json configs[3] quotes 85 M rows (README.md:138 of the
+    reference), row-sharded across 8 GPUs."""
     f = [(f"D{i}", "dense", 0, 1) for i in range(8)]
-    f += [(f"s{i}", "sparse", max(2, v // scale), embed_dim) for i, v in enumerate(ALI_VOCAB)]
+    f += [(f"s{i}", "sparse", (item_rows if (item_rows and i == 9) else max(2, v // scale)), embed_dim) for i, v in enumerate(ALI_VOCAB)]
     return f
 
 
-def kuairand_features(big=4_000_000 // 8):
+def kuairand_features(big=4_000_000):
     vocab = [big, 1000] + [50 + 45 * i for i in range(30)]
     return [(f"s{i}", "sparse", v, 16) for i, v in enumerate(vocab)] + [(f"D{i}", "dense", 0, 1) for i in range(4)]
 
@@ -33,10 +35,10 @@ def mind_features(scale=1):
     return [("user", "sparse", 748_000 // scale, 64), ("item", "sparse", 20_000 // scale, 64), ("cat", "sparse", 300, 64)]
 
 
-def _ali_split():
+def _ali_split(item_rows=None):
     """PPNet / EPNet feature split of scripts/run_ali_ccp_ctr_ranking_multi_domain.py:155-158 of the
     reference: id = user + item fields, scenario = field '301' (s18 here, vocab 3), agnostic = the rest."""
-    feats = ali_ccp_features()
+    feats = ali_ccp_features(item_rows=item_rows)
     by = {f[0]: f for f in feats}
     idf = [by["s0"], by["s9"]]
     sce = [by["s18"]]
@@ -44,10 +46,19 @@ def _ali_split():
     return idf, sce, agn
 
 
+ITEM_85M = 85_000_000
+
+
 def _cases():
     idf, sce, agn = _ali_split()
+    idf85, sce85, agn85 = _ali_split(ITEM_85M)
     deep = [256, 128, 64, 32, 16, 8]
     return {
+        # BASELINE.json configs[3]: the 85 M-row item table (5.44 GB fp32), row-sharded when run on several GPUs
+        "cfg4a_star_aliccp85m_b4096": ("Star", dict(features=ali_ccp_features(item_rows=ITEM_85M), domain_num=3, fcn_dims=deep, aux_dims=[16]), 4096),
+        "cfg4b_ppnet_aliccp85m_b4096": ("PPNet", dict(id_features=idf85, agn_features=agn85 + sce85, domain_num=3, fcn_dims=deep), 4096),
+        "cfg2_mmoe_aliccp85m_b4096": ("MMOE", dict(features=ali_ccp_features(item_rows=ITEM_85M), domain_num=3, n_expert=4, expert_dims=deep,
+                                                   tower_dims=[16]), 4096),
         # name: (model, cfg, B)
         "cfg1_sharedbottom_ml1m_b256": ("SharedBottom", dict(features=ml1m_features(), domain_num=3, bottom_dims=[128],
                                                              tower_dims=[8]), 256),
