@@ -233,8 +233,13 @@ def run_reference(args, rank, world):
 # --------------------------------------------------------------------------------------------
 # op costs (algorithmic bytes / flops) from the step's records
 # --------------------------------------------------------------------------------------------
+FAMILY = {"fc_fwd": "fc_fwd", "fc_dgrad": "fc_dgrad", "fc_wgrad": "fc_wgrad", "fc_presplit": "fc_presplit", "gather": "gather", "scatter": "scatter",
+          "adam": "optimizer", "adam_rows": "optimizer", "adam_flush": "optimizer", "zero": "optimizer"}
+
+
 def op_table(recs, B, feats):
-    """header index -> dict(name, bound, work) for every op of a record list."""
+    """header index -> dict(name, family, bound, work) for every op of a record list.  work = algorithmic bytes (HBM-bound
+    ops) or fp32 FLOPs (FC ops: 2 * B * K * N per group; not multiplied by the 3x of the operand split)."""
     from scenario_wise_rec_b200 import _native as N
     names = {getattr(N, k): k[3:].lower() for k in dir(N) if k.startswith("OP_")}
     i64 = lambda r: (int(r["i"][0]) & 0xFFFFFFFF) | (int(r["i"][1]) << 32)      # noqa: E731
@@ -244,10 +249,13 @@ def op_table(recs, B, feats):
         h = recs[i]
         kind, ns = int(h["kind"]), int(h["n_sub"])
         subs = recs[i + 1:i + 1 + ns]
-        d = {"name": names.get(kind, str(kind)), "bound": "hbm", "work": None}
+        base = names.get(kind, str(kind))
+        d = {"name": base, "family": FAMILY.get(base, base), "bound": "hbm", "work": None}
         if kind in (N.OP_FC_FWD, N.OP_FC_DGRAD, N.OP_FC_WGRAD):
-            fl = sum(2.0 * B * int(r["i"][1]) * int(r["i"][5]) for r in subs)
-            d.update(bound="tensor", work=fl, name=f"{d['name']}[{ns}g K{int(subs[0]['i'][1])} N{int(subs[0]['i'][5])}]")
+            fl = sum(2.0 * B * int(r["i"][13] if int(r["i"][13]) > 0 else r["i"][1]) * int(r["i"][5]) for r in subs)
+            d.update(bound="tensor", work=fl, name=f"{base}[{ns}g K{int(subs[0]['i'][1])} N{int(subs[0]['i'][5])}]")
+        elif kind == N.OP_FC_PRESPLIT:
+            d["work"] = float(sum(4.0 * int(r["i"][1]) * int(r["i"][5]) * 5 for r in subs))      # read W, write 2 planes x 2 orientations
         elif kind == N.OP_GATHER:
             d["work"] = float(B * workloads.gather_bytes_per_sample(feats))
         elif kind == N.OP_SCATTER:
@@ -258,14 +266,21 @@ def op_table(recs, B, feats):
         elif kind == N.OP_ADAM:
             d["work"] = 28.0 * i64(h)          # read p, g, m, v; write p, m, v (fp32)
             d["name"] = f"adam[{i64(h) / 1e6:.2f}M]"
+        elif kind == N.OP_ADAM_ROWS:
+            # per looked-up row: read p, g, m, v and write p, m, v (+ zero g) = 32 B per element, + index and bookkeeping
+            d["work"] = float(sum(B * (32.0 * int(r["i"][5]) + 16.0) for r in subs))
+            d["name"] = "adam_rows[%s]" % ("catch-up" if int(h["i"][1]) == 0 else "update")
+        elif kind == N.OP_ADAM_FLUSH:
+            d["work"] = float(sum(24.0 * i64(r) * int(r["i"][5]) for r in subs))
         out[i] = d
         i += 1 + ns
     return out
 
 
-def saturated_gather_scatter(feats, dev, pk, lookups_log2=18):
-    """K1 / K2 through the raw C ABI at a size that fills the machine (2^18 batch rows x every sparse field of the
-    workload = ~6 M lookups per launch), fresh random indices per launch, CUDA events on the launch stream."""
+def saturated_gather_scatter(feats, dev, pk, lookups_log2=18, min_table_bytes=1.5e9):
+    """K1 / K2 through the raw C ABI at a size that fills the machine: 2^18 batch rows x every sparse field of the workload
+    (~6 M lookups per launch), on tables scaled up until they hold >= 1.5 GB (an order of magnitude beyond the 126 MB L2, so
+    the rows really come from HBM), fresh random indices per launch, CUDA events on the launch stream."""
     import ctypes
     from scenario_wise_rec_b200 import _native as N
     sp = [(v, d) for _, k, v, d in feats if k == "sparse"]
@@ -273,6 +288,9 @@ def saturated_gather_scatter(feats, dev, pk, lookups_log2=18):
     E = sp[0][1]
     if any(d != E for _, d in sp):
         return None
+    scale = max(1, int(np.ceil(min_table_bytes / sum(v * d * 4 for v, d in sp))))
+    sp = [(v * scale if v >= 1000 else v, d) for v, d in sp]        # tiny fields stay tiny (they live in cache anyway)
+    tbytes = sum(v * d * 4 for v, d in sp)
     Bs = 1 << lookups_log2
     g = torch.Generator(device=dev).manual_seed(17)
     tables = [torch.randn(v, E, device=dev, generator=g) for v, _ in sp]
@@ -296,7 +314,7 @@ def saturated_gather_scatter(feats, dev, pk, lookups_log2=18):
     def scatter(i):
         N.check(L.swr_embedding_scatter_bwd(out.data_ptr(), IN, Bs, arr(sets[i % 4]), idt, arr(gtabs), vocab, len(sp), E, st), "scatter")
 
-    res = {}
+    res = {"table_bytes": tbytes, "note": "tables scaled x%d to %.2f GB (L2 is 126 MB)" % (scale, tbytes / 1e9)}
     for name, fn, per in (("gather", gather, workloads.gather_bytes_per_sample(feats)), ("scatter", scatter, workloads.scatter_bytes_per_sample(feats))):
         for i in range(3):
             fn(i)
@@ -309,7 +327,10 @@ def saturated_gather_scatter(feats, dev, pk, lookups_log2=18):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         gbps = per * Bs / ms / 1e6
-        res[name] = {"rows": Bs, "lookups": Bs * len(sp), "ms": ms, "GBps": gbps, "frac_hbm": gbps / pk["hbm"]}
+        res[name] = {"rows": Bs, "lookups": Bs * len(sp), "ms": ms, "GBps": gbps, "frac_hbm": gbps / pk["hbm"],
+                     "traffic": ncu_traffic(name + "_saturated")}
+    del tables, gtabs, sets, out
+    torch.cuda.empty_cache()
     return res
 
 
@@ -323,6 +344,59 @@ def ncu_traffic(op_name):
         return json.load(open(f)).get(op_name)
     except Exception:
         return None
+
+
+def measure_scopes(trainer, fs, model, devb, host, B, dev, iters=100):
+    """SURVEY.md 8d scopes beside the full train step: (ii) forward + BCELoss + backward without the optimizer, (iii) the
+    evaluation forward (eval-mode program: running statistics, no gradient buffers).  Each scope is captured in a CUDA graph
+    and replayed on device-resident batches, CUDA-event timed."""
+    from scenario_wise_rec_b200 import _native as N
+    out = {}
+    side = torch.cuda.Stream(dev)
+
+    def timed_graph(body, prep=None):
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                body()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            body()
+        torch.cuda.synchronize()
+        for _ in range(5):
+            g.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(iters):
+            if prep is not None:
+                prep(i)
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    # (ii) forward + loss + backward: the step's own records minus the optimizer ops
+    recs = fs.scope_records("fwd_bwd")
+    st = lambda: torch.cuda.current_stream(dev).cuda_stream      # noqa: E731
+
+    def prep(i):
+        N.memcpy_async(fs.dev_stage.data_ptr(), devb[i % len(devb)].buf.data_ptr(), fs.stage_bytes, st())
+    ms = timed_graph(lambda: N.program_run(recs, fs.ptrs, st()), prep)
+    fs.restore_after_scope()
+    out["fwd_bwd"] = {"ms": ms, "samples_per_s": B / ms * 1e3}
+    # (iii) evaluation forward
+    was = model.training
+    model.eval()
+    xd = {k: v.to(dev) for k, v in host[0][0].items()}
+    with torch.no_grad():
+        runner = model._runner(xd)
+        runner._bind_inputs(xd)
+        ms = timed_graph(lambda: N.program_run(runner.prog.recs_fwd, runner.ptrs, st()))
+    model.train(was)
+    out["eval_fwd"] = {"ms": ms, "samples_per_s": B / ms * 1e3, "launches": int(runner.prog.n_launch_fwd)}
+    return out
 
 
 # --------------------------------------------------------------------------------------------
@@ -352,6 +426,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=workloads.DEFAULT_CASE, choices=sorted(workloads.CASES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-saturated", action="store_true", help="skip the saturated K1 / K2 measurement (1.5 GB of tables)")
+    ap.add_argument("--no-scopes", action="store_true", help="skip the fwd+bwd / eval-forward scopes")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--ref-budget", type=float, default=60.0, help="seconds of CPU work for --impl reference")
     ap.add_argument("--eager-budget", type=float, default=6.0, help="seconds for the eager-CUDA run of the unmodified reference")
@@ -447,36 +523,64 @@ def main():
     run_resident(P)
     kinds, recs, opms = N.profile_end()
     fs.use_graph = True
-    tab = op_table(fs.recs_a, B, feats)
-    tab_b = op_table(fs.recs_b, B, feats) if fs.recs_b is not None else {}
+    tabs = [(fs.recs_a, op_table(fs.recs_a, B, feats))]
+    if fs.recs_b is not None:
+        tabs.append((fs.recs_b, op_table(fs.recs_b, B, feats)))
+    if getattr(fs, "_flush_recs", None) is not None:
+        tabs.append((fs._flush_recs, op_table(fs._flush_recs, B, feats)))
     agg = {}
     for k, r, t in zip(kinds.tolist(), recs.tolist(), opms.tolist()):
-        src = tab if (r in tab and int(fs.recs_a[r]["kind"]) == k) else tab_b
-        agg.setdefault((id(src), r), [src.get(r, {"name": str(k), "bound": "hbm", "work": None}), []])[1].append(t)
+        d = None
+        for ti, (rl, tb) in enumerate(tabs):
+            if r in tb and r < len(rl) and int(rl[r]["kind"]) == k:
+                d, key = tb[r], (ti, r)
+                break
+        if d is None:
+            d, key = {"name": str(k), "family": str(k), "bound": "hbm", "work": None}, (-1, k)
+        agg.setdefault(key, [d, []])[1].append(t)
     pk = peaks()
-    ops = [{"op": d["name"], "ms": float(np.mean(ts)), "bound": d["bound"], "work": d["work"]} for d, ts in agg.values()]
+    # per op: mean device time per STEP (an op that runs every 32nd step, the lazy-Adam flush, is amortised)
+    ops = [{"op": d["name"], "family": d["family"], "ms": float(np.sum(ts)) / P, "bound": d["bound"], "work": d["work"],
+            "runs_per_step": len(ts) / P} for d, ts in agg.values()]
     ops.sort(key=lambda o: -o["ms"])
-    top = ops[0]
-    if top["bound"] == "tensor":
-        ach = top["work"] / (top["ms"] * 1e-3) / 1e12 if top["work"] else None
-        roof = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": (ach / pk["bf16_sustained"]) if ach else None, "traffic": None}
-    else:
-        ach = top["work"] / (top["ms"] * 1e-3) / 1e9 if top["work"] else None
-        roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": (ach / pk["hbm"]) if ach else None, "traffic": None}
-    roof.update(kernel=top["op"], kernel_ms=top["ms"], peak_source=pk["source"],
-                share_of_step=top["ms"] / max(sum(o["ms"] for o in ops), 1e-9), traffic=ncu_traffic(top["op"]))
-    # the top tensor-bound op as well (the dominant kernel may be the HBM-bound optimizer sweep)
-    ttop = next((o for o in ops if o["bound"] == "tensor" and o["work"]), None)
-    roof_t = None
-    if ttop is not None:
-        ach_t = ttop["work"] / (ttop["ms"] * 1e-3) / 1e12
-        roof_t = {"bound": "tensor", "kernel": ttop["op"], "kernel_ms": ttop["ms"], "achieved": ach_t, "peak": pk["bf16_sustained"],
-                  "unit": "TFLOP/s", "frac": ach_t / pk["bf16_sustained"], "traffic": ncu_traffic(ttop["op"]),
-                  "note": "algorithmic fp32 FLOPs; the 3xTF32 arithmetic issues 3x that on a pipe with half the bf16 rate"}
-    sat = saturated_gather_scatter(feats, dev, pk) if rank == 0 else None
+    step_ms = max(sum(o["ms"] for o in ops), 1e-9)
+    fams = {}
+    for o in ops:
+        f = fams.setdefault(o["family"], {"ms": 0.0, "work": 0.0, "bound": o["bound"], "launches": 0.0, "ops": []})
+        f["ms"] += o["ms"]
+        f["work"] += (o["work"] or 0.0) * o["runs_per_step"]
+        f["launches"] += o["runs_per_step"]
+        f["ops"].append(o["op"])
+
+    def roofline_of(name, f):
+        if f["bound"] == "tensor":
+            ach = f["work"] / (f["ms"] * 1e-3) / 1e12
+            r = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
+                 "note": "algorithmic fp32 FLOPs (2 B K N per layer) over the summed device time of every launch of the kernel; the "
+                         "3xTF32 arithmetic issues 3x that on a pipe with half the bf16 rate, so 1/6 of the peak is this arithmetic's ceiling"}
+        else:
+            ach = f["work"] / (f["ms"] * 1e-3) / 1e9
+            r = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
+        r.update(kernel=name, launches_per_step=f["launches"], kernel_ms_per_step=f["ms"], share_of_step=f["ms"] / step_ms,
+                 peak_source=pk["source"], traffic=ncu_traffic(name), ops=f["ops"][:8])
+        return r
+    # the dominant kernel FUNCTION of the hot path (gather / FC stack / scatter), summed over its launches; the optimizer
+    # (a section-8f op) is reported beside it
+    hot = {k: v for k, v in fams.items() if k in ("fc_fwd", "fc_dgrad", "fc_wgrad", "gather", "scatter") and v["work"]}
+    top_name = max(hot, key=lambda k: hot[k]["ms"])
+    roof = roofline_of(top_name, hot[top_name])
+    roof_by_kernel = {k: {kk: vv for kk, vv in roofline_of(k, v).items() if kk in ("bound", "achieved", "peak", "unit", "frac", "kernel_ms_per_step",
+                                                                                  "launches_per_step", "share_of_step", "traffic")}
+                      for k, v in hot.items()}
+    roof_opt = roofline_of("optimizer", fams["optimizer"]) if "optimizer" in fams and fams["optimizer"]["work"] else None
+    sat = saturated_gather_scatter(feats, dev, pk) if (rank == 0 and not args.no_saturated) else None
     gather = next((o for o in ops if o["op"] == "gather"), None)
     scatter = next((o for o in ops if o["op"] == "scatter"), None)
+    scopes = measure_scopes(trainer, fs, model, devb, host, B, dev) if (world == 1 and not args.no_scopes) else None
+    parity = None
+    if world > 1:
+        import dist_parity
+        parity = dist_parity.run(dev)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -488,9 +592,12 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "roofline": roof,
-        "roofline_tensor": roof_t,
-        "ops_ms": [{"op": o["op"], "ms": round(o["ms"], 5)} for o in ops[:14]],
-        "ops_ms_total": round(sum(o["ms"] for o in ops), 5),
+        "roofline_by_kernel": roof_by_kernel,
+        "roofline_optimizer": roof_opt,
+        "scopes": scopes,
+        "dist_parity": parity,
+        "ops_ms": [{"op": o["op"], "ms": round(o["ms"], 5)} for o in ops[:16]],
+        "ops_ms_total": round(step_ms, 5),
         "gather": None if not gather else {"ms": gather["ms"], "GBps": gather["work"] / gather["ms"] / 1e6, "frac_hbm": gather["work"] / gather["ms"] / 1e6 / pk["hbm"]},
         "scatter": None if not scatter else {"ms": scatter["ms"], "GBps": scatter["work"] / scatter["ms"] / 1e6, "frac_hbm": scatter["work"] / scatter["ms"] / 1e6 / pk["hbm"]},
         "gather_scatter_saturated": sat,

@@ -126,12 +126,23 @@ struct LazyParams {
   float4* hist;             // [capacity] scalars per step, index s - ctrl[2]
 };
 
+// hist_s: the last kLazyWin steps' scalars staged in shared memory (hist_s[i] = step win0 + i); older steps come from
+// global memory (one dependent L2 access per replayed step, which is what made the first version of these kernels slow)
+constexpr int kLazyWin = 64;
 __device__ __forceinline__ void lazy_replay(float& P, float& M, float& V, int from, int to, const float4* hist, int base,
-                                            float b1, float b2, float eps) {
+                                            const float4* hist_s, int win0, float b1, float b2, float eps) {
   for (int s = from; s <= to; ++s) {          // steps the row sat out: zero gradient
-    const float4 h = __ldg(hist + (s - base));
+    const float4 h = s >= win0 ? hist_s[s - win0] : __ldg(hist + (s - base));
     adam_elem(P, 0.f, M, V, h.x, b1, b2, eps, h.z, h.y);
   }
+}
+// stage hist[max(base, t - kLazyWin + 1) .. t] (entry t only if `with_t`) ; returns win0
+__device__ __forceinline__ int lazy_stage_hist(float4* hist_s, const float4* hist, int base, int t, bool with_t) {
+  const int win0 = max(base, t - kLazyWin + 1);
+  const int last = with_t ? t : t - 1;
+  for (int s = win0 + (int)threadIdx.x; s <= last; s += blockDim.x) hist_s[s - win0] = __ldg(hist + (s - base));
+  __syncthreads();
+  return win0;
 }
 
 // phase 0: catch-up to t - 1;  phase 1: (catch-up +) step t with the gradient row, gradient row zeroed
@@ -139,36 +150,76 @@ template <int PHASE>
 __global__ void __launch_bounds__(256) adam_rows_kernel(const __grid_constant__ LazyParams p) {
   const int t = p.ctrl[1], base = p.ctrl[2];
   const float b1 = __ldg(p.hyper + 1), b2 = __ldg(p.hyper + 2), eps = __ldg(p.hyper + 3);
-  if (PHASE == 1 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+  if (PHASE == 1 && blockIdx.x == 0 && threadIdx.x == 0)
     p.hist[t - base] = make_float4(__ldg(p.hyper + 0), __ldg(p.hyper + 5), __ldg(p.hyper + 4), 0.f);
-  const LazyField& F = p.f[blockIdx.y];
-  const int E = F.E, lanes = E < 32 ? E : 32;            // E <= 32: one row per `E` lanes; wider rows: a warp strides over it
-  const int per_warp = 32 / lanes;
-  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int sub = lane / lanes, l = lane - sub * lanes;
-  const int n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (int b0 = warp_global * per_warp; b0 < p.B; b0 += n_warps * per_warp) {
-    const int b = b0 + sub;
+  __shared__ float4 hist_s[kLazyWin];
+  const int win0 = lazy_stage_hist(hist_s, p.hist, base, t, false);
+  // One grid-stride loop over every (field, batch row) lookup of the launch (a single wave of CTAs).  E <= 32: one row
+  // per `E` lanes (E = 16: two lookups per warp pass); wider rows: a warp strides over the row.
+  const int E = p.f[0].E, lanes = E < 32 ? E : 32, per_warp = 32 / lanes;      // every field of a launch shares E (host checks)
+  const int lane = threadIdx.x & 31, sub = lane / lanes, l = lane - sub * lanes;
+  const int64_t total = (int64_t)p.n_fields * p.B;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * per_warp; i0 < total; i0 += n_warps * per_warp) {
+    const int64_t i = i0 + sub;
+    const bool in = i < total && sub < per_warp;
+    const int f = in ? (int)(i / p.B) : 0;
+    const LazyField& F = p.f[f];
     int64_t r = -1;
-    int old = 0x7fffffff;
-    if (b < p.B && sub < per_warp) {
-      r = load_index(F.idx, F.idx_dtype, b);
+    if (in) {
+      r = load_index(F.idx, F.idx_dtype, i - (int64_t)f * p.B);
       if (r < 0 || r >= F.vocab) r = -1;
-      if (r >= 0 && l == 0) old = atomicMax(F.claim + r, 2 * t + PHASE);
+    }
+    // everything the owner of the row needs is requested at once; a lookup that turns out not to own the row (a
+    // duplicate inside the batch) has read one row in vain
+    int old = 0x7fffffff, last = 0;
+    float P[2] = {0.f, 0.f}, M[2] = {0.f, 0.f}, V[2] = {0.f, 0.f}, G[2] = {0.f, 0.f};
+    if (r >= 0) {
+      if (l == 0) old = __ldcg(F.claim + r);
+      last = __ldcg(F.last + r);
+      if (E <= 64) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int e = l + k * lanes;
+          if (e < E) {
+            const int64_t o = r * E + e;
+            P[k] = F.p[o]; M[k] = F.m[o]; V[k] = F.v[o];
+            if (PHASE == 1) G[k] = F.g[o];
+          }
+        }
+      }
+      // hot rows (a 3-row table is looked up by the whole batch): only lookups that still see the row unclaimed pay for
+      // an atomic on its claim word
+      if (l == 0 && old < 2 * t + PHASE) old = atomicMax(F.claim + r, 2 * t + PHASE);
     }
     old = __shfl_sync(0xffffffffu, old, (sub * lanes) & 31);
     const bool own = r >= 0 && old < 2 * t + PHASE;       // in range, and no other lookup of the batch owns the row
     if (own) {
-      const int last = F.last[r];
-      for (int e = l; e < E; e += lanes) {
-        const int64_t o = r * E + e;
-        float P = F.p[o], M = F.m[o], V = F.v[o];
-        lazy_replay(P, M, V, last + 1, t - 1, p.hist, base, b1, b2, eps);
-        if (PHASE == 1) {
-          adam_elem(P, F.g[o], M, V, __ldg(p.hyper + 0), b1, b2, eps, __ldg(p.hyper + 4), __ldg(p.hyper + 5));
-          F.g[o] = 0.f;
+      if (E <= 64) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int e = l + k * lanes;
+          if (e < E) {
+            const int64_t o = r * E + e;
+            lazy_replay(P[k], M[k], V[k], last + 1, t - 1, p.hist, base, hist_s, win0, b1, b2, eps);
+            if (PHASE == 1) {
+              adam_elem(P[k], G[k], M[k], V[k], __ldg(p.hyper + 0), b1, b2, eps, __ldg(p.hyper + 4), __ldg(p.hyper + 5));
+              F.g[o] = 0.f;
+            }
+            F.p[o] = P[k]; F.m[o] = M[k]; F.v[o] = V[k];
+          }
         }
-        F.p[o] = P; F.m[o] = M; F.v[o] = V;
+      } else {
+        for (int e = l; e < E; e += lanes) {
+          const int64_t o = r * E + e;
+          float Pe = F.p[o], Me = F.m[o], Ve = F.v[o];
+          lazy_replay(Pe, Me, Ve, last + 1, t - 1, p.hist, base, hist_s, win0, b1, b2, eps);
+          if (PHASE == 1) {
+            adam_elem(Pe, F.g[o], Me, Ve, __ldg(p.hyper + 0), b1, b2, eps, __ldg(p.hyper + 4), __ldg(p.hyper + 5));
+            F.g[o] = 0.f;
+          }
+          F.p[o] = Pe; F.m[o] = Me; F.v[o] = Ve;
+        }
       }
     }
     __syncwarp();
@@ -182,13 +233,15 @@ __global__ void __launch_bounds__(256) adam_flush_kernel(float* __restrict__ P, 
                                                          const int32_t* __restrict__ ctrl, const float4* __restrict__ hist) {
   const int t = ctrl[1], base = ctrl[2];
   const float b1 = __ldg(hyper + 1), b2 = __ldg(hyper + 2), eps = __ldg(hyper + 3);
+  __shared__ float4 hist_s[kLazyWin];
+  const int win0 = lazy_stage_hist(hist_s, hist, base, t, true);
   const int64_t n = vocab * E;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / E;
     const int from = last[r] + 1;
     if (from > t) continue;
     float p = P[i], m = M[i], v = V[i];
-    lazy_replay(p, m, v, from, t, hist, base, b1, b2, eps);
+    lazy_replay(p, m, v, from, t, hist, base, hist_s, win0, b1, b2, eps);
     P[i] = p; M[i] = m; V[i] = v;
   }
 }
@@ -202,19 +255,21 @@ int launch_adam_rows(const LazyField* fields, int n_fields, int64_t B, const flo
                      cudaStream_t st) {
   if (n_fields <= 0 || B <= 0) return SWR_OK;
   if (!hyper || !ctrl || !hist) { set_error("adam_rows: null operand"); return SWR_ERR_INVALID; }
-  for (int o = 0; o < n_fields; o += kLazyMax) {
+  int o = 0;
+  while (o < n_fields) {       // one launch per run of fields with the same embedding width (normally: one launch)
     LazyParams p{};
-    p.n_fields = n_fields - o < kLazyMax ? n_fields - o : kLazyMax;
-    for (int i = 0; i < p.n_fields; ++i) {
-      p.f[i] = fields[o + i];
-      if (!p.f[i].p || !p.f[i].g || !p.f[i].m || !p.f[i].v || !p.f[i].last || !p.f[i].claim || !p.f[i].idx) { set_error("adam_rows: null field operand"); return SWR_ERR_INVALID; }
+    const int E0 = fields[o].E;
+    while (o < n_fields && p.n_fields < kLazyMax && fields[o].E == E0) {
+      p.f[p.n_fields] = fields[o++];
+      const LazyField& F = p.f[p.n_fields++];
+      if (!F.p || !F.g || !F.m || !F.v || !F.last || !F.claim || !F.idx || F.E <= 0) { set_error("adam_rows: bad field operand"); return SWR_ERR_INVALID; }
     }
     p.B = (int)B; p.hyper = hyper; p.ctrl = ctrl; p.hist = hist;
-    const int E0 = p.f[0].E, per_block = 8 * (E0 < 32 ? 32 / E0 : 1);
-    int gx = (int)((B + per_block - 1) / per_block);
-    if (gx > 4 * 148) gx = 4 * 148;
-    if (phase == 0) adam_rows_kernel<0><<<dim3(gx, p.n_fields), 256, 0, st>>>(p);
-    else adam_rows_kernel<1><<<dim3(gx, p.n_fields), 256, 0, st>>>(p);
+    const int64_t per_block = 8 * (E0 < 32 ? 32 / E0 : 1);
+    int64_t gx = ((int64_t)p.n_fields * B + per_block - 1) / per_block;
+    if (gx > 148 * 8) gx = 148 * 8;      // one wave (256 threads, 8 CTAs per SM)
+    if (phase == 0) adam_rows_kernel<0><<<(int)gx, 256, 0, st>>>(p);
+    else adam_rows_kernel<1><<<(int)gx, 256, 0, st>>>(p);
     SWR_LAUNCH_OK("adam_rows_kernel");
   }
   return SWR_OK;

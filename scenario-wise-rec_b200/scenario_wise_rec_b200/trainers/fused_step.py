@@ -174,7 +174,7 @@ class LazyTables:
         self.last = torch.full((max(rows, 1),), flat.step, dtype=torch.int32, device=dev)
         self.claim = torch.zeros(max(rows, 1), dtype=torch.int32, device=dev)
         self.hist = torch.zeros(4 * self.HIST_CAP, dtype=torch.float32, device=dev)
-        self.flush_every = max(1, int(os.environ.get("SWR_LAZY_FLUSH", "32")))
+        self.flush_every = max(1, int(os.environ.get("SWR_LAZY_FLUSH", "64")))      # measured at cfg2: 8 -> 0.637, 32 -> 0.610, 64 -> 0.606 ms / step
         self.dirty = False
         self._flush_recs = None
         self._flush_ptrs = None
@@ -610,6 +610,27 @@ class FusedTrainStep:
         h = LossHandle(self, self.k)
         self.k += 1
         return h
+
+    def scope_records(self, scope: str):
+        """Record list of a sub-scope of the step for measurements (bench.py): ``fwd_bwd`` = forward program, BCELoss,
+        gradient zero-fill, backward program -- no optimizer op.  Call ``restore_after_scope`` afterwards."""
+        if scope != "fwd_bwd":
+            raise KeyError(scope)
+        opt_kinds = (N.OP_ADAM, N.OP_ADAM_ROWS, N.OP_ADAM_FLUSH)
+        keep, i = [], 0
+        recs = self.recs_a
+        while i < len(recs):
+            ns = int(recs[i]["n_sub"])
+            if int(recs[i]["kind"]) not in opt_kinds:
+                keep.extend(range(i, i + 1 + ns))
+            i += 1 + ns
+        return np.ascontiguousarray(recs[keep])
+
+    def restore_after_scope(self):
+        """The optimizer-free scope leaves gradients behind; the lazy table update relies on an all-zero table-gradient arena."""
+        for a in self.g.values():
+            a.zero_()
+        torch.cuda.synchronize(self.device)
 
     def _flush_lazy(self):
         """Replay every postponed row update up to the current step (device work on the current stream)."""

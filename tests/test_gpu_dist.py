@@ -16,3 +16,11 @@ def test_two_gpu_dp_and_sharded_tables():
            "--master-port", "29533", os.path.join(HERE, "dist_gpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "DIST_GPU_CHECK_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-6000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_two_gpu_peer_memory_shards():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29534", os.path.join(HERE, "dist_p2p_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "DIST_P2P_CHECK_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-6000:]

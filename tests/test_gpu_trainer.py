@@ -271,3 +271,43 @@ def test_lazy_adam_matches_the_dense_trajectory(monkeypatch):
                 torch.testing.assert_close(od[pid]["exp_avg"], st["exp_avg"], atol=1e-6, rtol=2e-3)
                 torch.testing.assert_close(od[pid]["exp_avg_sq"], st["exp_avg_sq"], atol=1e-9, rtol=2e-3)
                 assert float(od[pid]["step"]) == float(st["step"]) == steps
+
+
+def test_cfg2_trajectory_20_steps_vs_cpu_oracle():
+    """BASELINE.json configs[1] (MMoE, Ali-CCP shape, B = 4096) in the default FC mode (tensor-core kernels on the wide layers,
+    row-lazy Adam on the tables): 20 fused steps against the CPU oracle + torch.optim.Adam on the same batches; the loss
+    must agree within 1e-4 at every step."""
+    import workloads
+    model_name, cfg, B = workloads.CASES["cfg2_mmoe_aliccp_b4096"]
+    feats = workloads.all_feature_specs(cfg)
+    torch.manual_seed(5)
+    m = model_factory.build(model_name, cfg)
+    state = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    t = CTRTrainer(m, "cfg2", optimizer_params={"lr": 1e-3, "weight_decay": 1e-5}, device=DEV)
+    m.train()
+    st = {}
+    for k, v in state.items():
+        v = v.clone()
+        if v.dtype.is_floating_point and "running_" not in k:
+            v.requires_grad_(True)
+        st[k] = v
+    params = [v for v in st.values() if v.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-3, weight_decay=1e-5)
+    worst = 0.0
+    for i in range(20):
+        x, y = workloads.make_batch(feats, B, cfg["domain_num"], seed=300 + i)
+        loss = t.train_step(x, y).item()
+        bn_out = {}
+        out = ref_models.forward(model_name, x, st, cfg, training=True, bn_out=bn_out)
+        ref_loss = ref_models.bce_loss(out, y)
+        for p in params:
+            p.grad = None
+        ref_loss.backward()
+        opt.step()
+        with torch.no_grad():
+            for k, v in bn_out.items():
+                st[k] = v
+        worst = max(worst, abs(loss - float(ref_loss.detach())))
+        assert abs(loss - float(ref_loss.detach())) <= 1e-4, (i, loss, float(ref_loss.detach()))
+    fs = next(iter(t._steps.values()))
+    assert fs.graph is not None and fs.lazy is not None

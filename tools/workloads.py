@@ -71,6 +71,9 @@ def _cases():
         "cfg4c_epnet_aliccp_b4096": ("EPNet", dict(sce_features=sce, agn_features=agn, domain_num=3, fcn_dims=deep), 4096),
         "cfg5a_hamursmall_mind_b16384": ("HamurSmall", dict(features=mind_features(), domain_num=4, fcn_dims=[256, 128],
                                                             hyper_dims=[64], k=35), 16384),
+        # HamurLarge at the Ali-CCP shape (hamur.py:101-244: seven backbone layers, two adapter cells, k = 65)
+        "cfg5c_hamurlarge_aliccp_b2048": ("HamurLarge", dict(features=ali_ccp_features(), domain_num=3, fcn_dims=[256, 256, 128, 128, 64, 64, 32],
+                                                             hyper_dims=[64], k=65), 2048),
         "cfg5b_m3oe_mind_b16384": ("M3oE", dict(features=mind_features(), domain_num=4, fcn_dims=[128, 64, 64, 32],
                                                 expert_num=4), 16384),
     }
