@@ -690,27 +690,6 @@ static int launch_fc_skinny_fwd(const FcGroup* groups, int n_groups, int64_t B, 
   return SWR_OK;
 }
 
-// SWR_FC_AUTO: groups too narrow to fill a 128 x N accumulator tile (gates, towers' last layers) stay on the
-// FFMA kernels -- as CTAs of the tensor-core launch they would each hold a whole SM for a sliver of work.
-static bool tc_narrow(const FcGroup& g) { return g.Y.n < 32; }
-
-template <class F1, class F2>
-static int split_by_width(const FcGroup* groups, int n_groups, F1 run_tc, F2 run_simt) {
-  FcGroup wide[kMaxGroups], narrow[kMaxGroups];
-  int nw = 0, nn = 0;
-  for (int g = 0; g < n_groups; ++g) {
-    if (fc_mode_get() == SWR_FC_AUTO && tc_narrow(groups[g])) narrow[nn++] = groups[g];
-    else wide[nw++] = groups[g];
-  }
-  if (nn) { int rc = run_simt(narrow, nn); if (rc) return rc; }
-  if (nw) {
-    int rc = run_tc(wide, nw);
-    if (rc == SWR_ERR_UNSUPPORTED) rc = run_simt(wide, nw);   // a shape the tensor-core tiles cannot hold: FFMA serves everything
-    if (rc) return rc;
-  }
-  return SWR_OK;
-}
-
 static int launch_fc_fwd_simt(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st);
 static int launch_fc_wgrad_simt(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st);
 
@@ -722,10 +701,8 @@ int launch_fc_fwd(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t s
     rc = launch_fc_tc2_fwd(groups, n_groups, B, st);     // every group of the level, narrow ones included, in one launch
     if (rc != SWR_ERR_UNSUPPORTED) return rc;
   }
-  if (fc_tc_wanted(groups, n_groups, B))
-    return split_by_width(groups, n_groups, [&](const FcGroup* g, int n) { return launch_fc_tc_fwd(g, n, B, st); },
-                          [&](const FcGroup* g, int n) { return skinny_ok(g, n) ? launch_fc_skinny_fwd(g, n, B, st) : launch_fc_fwd_simt(g, n, B, st); });
-  return launch_fc_fwd_simt(groups, n_groups, B, st);
+  // shapes the tensor-core kernels do not take (unaligned column sub-views): FFMA serves them
+  return skinny_ok(groups, n_groups) ? launch_fc_skinny_fwd(groups, n_groups, B, st) : launch_fc_fwd_simt(groups, n_groups, B, st);
 }
 
 static int launch_fc_fwd_simt(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st) {
@@ -789,10 +766,6 @@ int launch_fc_dgrad(const FcGroup* groups, const int* dst_of, int n_groups, int6
     rc = launch_fc_tc2_dgrad(groups, p.dst_group, n_dst, n_groups, B, st);
     if (rc != SWR_ERR_UNSUPPORTED) return rc;
   }
-  if (fc_tc_wanted(groups, n_groups, B)) {
-    rc = launch_fc_tc_dgrad(groups, p.dst_group, n_dst, n_groups, B, st);
-    if (rc != SWR_ERR_UNSUPPORTED) return rc;   // else: a shape the tensor-core tiles cannot hold, FFMA serves it
-  }
   if (kd_max > 16) return tiles128 >= 296 ? run_dgrad<CfgWide>(p, st) : run_dgrad<CfgMid>(p, st);
   return run_dgrad<CfgNarrowS>(p, st);
 }
@@ -830,9 +803,6 @@ int launch_fc_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t
     rc = launch_fc_tc2_wgrad(groups, n_groups, B, st);
     if (rc != SWR_ERR_UNSUPPORTED) return rc;
   }
-  if (fc_tc_wanted(groups, n_groups, B))
-    return split_by_width(groups, n_groups, [&](const FcGroup* g, int n) { return launch_fc_tc_wgrad(g, n, B, st); },
-                          [&](const FcGroup* g, int n) { return launch_fc_wgrad_simt(g, n, B, st); });
   return launch_fc_wgrad_simt(groups, n_groups, B, st);
 }
 

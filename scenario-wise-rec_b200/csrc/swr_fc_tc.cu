@@ -1,4 +1,4 @@
-// swr_fc_tc2.cu -- grouped fully-connected kernels on the sm_100a tensor cores, second generation:
+// swr_fc_tc.cu -- grouped fully-connected kernels on the sm_100a tensor cores, second generation:
 // persistent, warp-specialised, TMA-fed.
 //
 // Same contract as the FFMA kernels in swr_fc.cu (fc_fwd / fc_dgrad / fc_wgrad over FcGroup lists; reference:
@@ -26,6 +26,7 @@
 #include "swr_launch.h"
 #include "swr_tc.cuh"
 #include <cuda.h>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1191,11 +1192,48 @@ static int t2_launch(K kernel, int n_tiles, int cluster, size_t smem, const Tc2P
   return SWR_OK;
 }
 
+// SWR_FC_SIMT / SWR_FC_TC / SWR_FC_AUTO (include/swr_b200.h); preset by env SWR_FC_TC, changed by swr_set_fc_mode()
+static std::atomic<int> g_tc_mode{-1};
+int fc_mode_get() {
+  int m = g_tc_mode.load();
+  if (m < 0) {
+    const char* e = getenv("SWR_FC_TC");
+    m = e ? atoi(e) : SWR_FC_AUTO;
+    if (m < 0 || m > 2) m = SWR_FC_AUTO;
+    g_tc_mode.store(m);
+  }
+  return m;
+}
+int fc_mode_set(int mode) {
+  const int prev = fc_mode_get();
+  if (mode >= 0 && mode <= 2) g_tc_mode.store(mode);
+  return prev;
+}
+static int tc_mode() { return fc_mode_get(); }
+static int64_t tc_min_macs() {
+  static int64_t v = -1;
+  if (v < 0) { const char* e = getenv("SWR_FC_TC_MIN_MACS"); v = e ? atoll(e) : (int64_t)1 << 24; }
+  return v;
+}
+
+bool fc_tc_wanted(const FcGroup* groups, int n_groups, int64_t B) {
+  const int mode = tc_mode();
+  if (mode == 0 || B < 64) return false;
+  int64_t macs = 0;
+  int kmax = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    macs += (int64_t)groups[g].A.n * groups[g].Y.n;
+    kmax = max(kmax, max(groups[g].A.n, groups[g].Y.n));
+  }
+  if (kmax > 4096) return false;   // coefficient tables live in shared memory
+  if (mode == 1) return true;
+  return macs * B >= tc_min_macs();
+}
+
+
 static inline bool is_al16_host(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 bool fc_tc2_usable(const FcGroup* groups, int n_groups, int pass) {
-  static const bool off = [] { const char* e = getenv("SWR_FC_TC_V1"); return e && atoi(e) != 0; }();
-  if (off) return false;
   for (int g = 0; g < n_groups; ++g) {
     const FcGroup& G = groups[g];
     const bool al = is_al16_host(G.A.raw) && (G.A.ld % 4 == 0) && is_al16_host(G.Y.raw) && (G.Y.ld % 4 == 0);

@@ -37,7 +37,7 @@ struct FcGroup {
   const float* bias; const float* bias2;  // effective bias = bias + bias2
   float* dW; float* dW2; float* dbias; float* dbias2;
   double* stats_out;    // [N][2] column moments of Y (train-mode BatchNorm), or null
-  const float* img_f;   // presplit weight images (swr_fc_tc2.cu): [2][N][K32] forward, [2][K][N32] data gradient; null = none
+  const float* img_f;   // presplit weight images (swr_fc_tc.cu): [2][N][K32] forward, [2][K][N32] data gradient; null = none
   const float* img_d;
   int k_full;           // input width of the layer's weight (A.n may be narrowed to the columns that receive a data gradient)
   int w_layout; int ldw;
@@ -53,10 +53,7 @@ int launch_fc_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t
 bool fc_tc_wanted(const FcGroup* groups, int n_groups, int64_t B);
 int fc_mode_get();
 int fc_mode_set(int mode);
-int launch_fc_tc_fwd(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st);
-int launch_fc_tc_dgrad(const FcGroup* groups, const int* dst_group, int n_dst, int n_groups, int64_t B, cudaStream_t st);
-int launch_fc_tc_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st);
-// second-generation tcgen05 path (swr_fc_tc2.cu): TMA-fed presplit weights, persistent warp-specialised kernels.
+// TMA-fed presplit weights, persistent warp-specialised kernels.
 // pass: 0 forward, 1 data gradient, 2 weight gradient
 bool fc_tc2_usable(const FcGroup* groups, int n_groups, int pass);
 int launch_fc_presplit(const FcGroup* groups, int n_groups, cudaStream_t st);

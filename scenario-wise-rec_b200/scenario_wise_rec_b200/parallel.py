@@ -50,6 +50,12 @@ def shard_features(features, min_rows: int = 1_000_000, group=None) -> List[str]
                 raise RuntimeError(f"feature {f.name!r} already owns a full table; shard before building the model")
             f.shard = info
             names.append(f.name)
+    by_name = {f.name: f for f in features if isinstance(f, SparseFeature)}
+    for f in features:          # a feature that shares a sharded table reads the same shards
+        if isinstance(f, SparseFeature) and f.shared_with is not None:
+            owner = by_name.get(f.shared_with)
+            if owner is not None and getattr(owner, "shard", None) is not None:
+                f.shard = owner.shard
     return names
 
 

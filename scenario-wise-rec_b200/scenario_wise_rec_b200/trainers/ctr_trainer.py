@@ -104,6 +104,7 @@ class CTRTrainer(object):
             if self._flat is None:
                 self._flat = fs.flat
                 self.optimizer.register_state_dict_pre_hook(lambda _opt: self._flat is not None and self._flat.publish_step())
+                self.optimizer.register_load_state_dict_post_hook(lambda _opt: self._flat is not None and self._flat.reload_optimizer_state())
                 if fs.flat.lazy is not None and not getattr(self.model, "_swr_lazy_hooks", False):
                     # row-lazy Adam: whatever reads the tables outside the fused step first gets every row replayed to
                     # the current step (generic forward = evaluation / prediction, state_dict = checkpoints, EarlyStopper)
@@ -170,6 +171,7 @@ class CTRTrainer(object):
                 self.scheduler.step()
             if val_dataloader:
                 auc, logloss = self.evaluate(self.model, val_dataloader)
+                auc = self._agree(auc)         # one process per GPU: every rank must take the same decision
                 print(f"epoch:{epoch_i} | val auc: {auc} | val logloss: {logloss}")
                 if self.early_stopper.stop_training(auc, self.model.state_dict()):
                     print(f"validation: best auc: {self.early_stopper.best_auc}")
@@ -180,14 +182,25 @@ class CTRTrainer(object):
         # same file as the reference writes (ctr_trainer.py:94-97).  With row-sharded tables the shards are gathered
         # back into full [vocab, E] tables under the reference's keys first, and one rank writes the file.
         from .. import parallel
-        if parallel._sharded_params(self.model):
-            import torch.distributed as dist
-            state = parallel.full_state_dict(self.model)
-            if dist.get_rank() != 0:
-                return
-        else:
-            state = self.model.state_dict()
-        torch.save(state, os.path.join(self.model_path, name))
+        import torch.distributed as dist
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        state = parallel.full_state_dict(self.model) if parallel._sharded_params(self.model) else self.model.state_dict()
+        if not multi or dist.get_rank() == 0:      # replicas are identical: one writer
+            torch.save(state, os.path.join(self.model_path, name))
+        if multi:
+            dist.barrier()
+
+    @staticmethod
+    def _agree(value):
+        """Under one process per GPU every rank validates on its own shard of the data; early stopping (and with it the
+        number of collectives each rank still issues) must not depend on the rank: the decision uses the mean over ranks."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return value
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t[0]) / dist.get_world_size()
 
     # ---- evaluation ------------------------------------------------------------------------------
     def _predict_batches(self, model, data_loader, desc):

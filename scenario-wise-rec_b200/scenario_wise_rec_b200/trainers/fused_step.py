@@ -88,6 +88,7 @@ class FlatArenas:
         self.m = {k: z(k) for k in self.opt_arenas}
         self.v = {k: z(k) for k in self.opt_arenas}
         self.params = []
+        self._entries = [e for e in entries + self.shards if e[1] != "virt"]
         step = 0
         with torch.no_grad():
             for p, a, off, n in entries + self.shards:
@@ -132,6 +133,28 @@ class FlatArenas:
         cur = [(id(p), a, off, n) for p, (a, off, n) in zip(prog.params, prog.param_arena)]
         strip = lambda lst: [e for e in lst if e[1] != "virt"]      # noqa: E731  (virtual tables are per batch size)
         return strip(cur) == strip(self.layout)
+
+    def reload_optimizer_state(self):
+        """After ``optimizer.load_state_dict()``: torch replaced the state tensors by fresh copies; copy them back into the
+        flat moment arenas and re-point ``optimizer.state`` at the arena views (the fused Adam kernels read the arenas)."""
+        step = 0
+        with torch.no_grad():
+            layout = {id(p): (a, off, n) for p, a, off, n in self._entries}
+            for p in self.params:
+                a, off, n = layout[id(p)]
+                st = self.optimizer.state.get(p)
+                if st and "exp_avg" in st and st["exp_avg"].data_ptr() != self.m[a][off:off + n].data_ptr():
+                    self.m[a][off:off + n].copy_(st["exp_avg"].reshape(-1))
+                    self.v[a][off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                if st and "step" in st:
+                    step = max(step, int(st["step"]))
+                self.optimizer.state[p] = {"step": torch.tensor(float(step)), "exp_avg": self.m[a][off:off + n].view(p.shape),
+                                           "exp_avg_sq": self.v[a][off:off + n].view(p.shape)}
+        self.step = step
+        if self.lazy is not None:       # every row is as current as the loaded state says
+            self.lazy.last.fill_(step)
+            self.lazy.base = step + 1
+            self.lazy.dirty = False
 
     def flush_lazy(self):
         """Bring every table row to the current step (no-op when nothing is postponed)."""

@@ -179,7 +179,7 @@ def test_baseline_shapes_vs_oracle(case, fc_mode):
         outliers = float(((ours - t).abs() > 5e-4 * scale).double().mean())
         flip = 2.0 / B ** 0.5
         # SWR_TEST_TC_STRICT=1 judges the tensor-core mode by the FFMA criteria below: with the accumulator flushes of
-        # swr_fc_tc2.cu 9 of the 11 cases pass them (round 1: 5 of 8); the two that do not are ReLU'(0) flips (a rank-1
+        # swr_fc_tc.cu 9 of the 11 cases pass them (round 1: 5 of 8); the two that do not are ReLU'(0) flips (a rank-1
         # change of one layer's weight gradient: many small outliers, rel-L2 7.5e-3)
         if not os.environ.get("SWR_TEST_TC_STRICT") and fc_mode != N.FC_SIMT and e_ours <= max(1e-2, 8 * e_ref, flip) and l2_ours <= max(1e-2, 4 * l2_ref, flip):
             continue
