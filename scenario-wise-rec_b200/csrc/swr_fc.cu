@@ -702,7 +702,10 @@ int launch_fc_fwd(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t s
     if (rc != SWR_ERR_UNSUPPORTED) return rc;
   }
   // shapes the tensor-core kernels do not take (unaligned column sub-views): FFMA serves them
-  return skinny_ok(groups, n_groups) ? launch_fc_skinny_fwd(groups, n_groups, B, st) : launch_fc_fwd_simt(groups, n_groups, B, st);
+  // (the skinny kernel pays off for gate-shaped layers: few outputs over a long contraction)
+  bool gate_like = skinny_ok(groups, n_groups);
+  for (int g = 0; g < n_groups; ++g) gate_like = gate_like && groups[g].A.n >= 128;
+  return gate_like ? launch_fc_skinny_fwd(groups, n_groups, B, st) : launch_fc_fwd_simt(groups, n_groups, B, st);
 }
 
 static int launch_fc_fwd_simt(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st) {

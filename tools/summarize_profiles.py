@@ -46,7 +46,7 @@ if os.path.exists(f):
     for r in rows[2:]:
         name = r[idx[0][1]]
         seen[name] += 1
-        if seen[name] > 3:
+        if seen[name] > 8:
             continue
         lines.append("| " + " | ".join((f"`{r[i][:60]}`" if w == "Kernel Name" else f"{r[i]} {U[i]}") for w, i in idx) + " |")
     lines.append("")
