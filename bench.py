@@ -573,7 +573,7 @@ def main():
                                                                                   "launches_per_step", "share_of_step", "traffic")}
                       for k, v in hot.items()}
     roof_opt = roofline_of("optimizer", fams["optimizer"]) if "optimizer" in fams and fams["optimizer"]["work"] else None
-    sat = saturated_gather_scatter(feats, dev, pk) if (rank == 0 and not args.no_saturated) else None
+    sat = saturated_gather_scatter(feats, dev, pk) if (world == 1 and not args.no_saturated) else None
     gather = next((o for o in ops if o["op"] == "gather"), None)
     scatter = next((o for o in ops if o["op"] == "scatter"), None)
     scopes = measure_scopes(trainer, fs, model, devb, host, B, dev) if (world == 1 and not args.no_scopes) else None

@@ -130,6 +130,7 @@ static int run_lazy_adam(const swr_rec_t& h, const swr_rec_t* subs, bool flush, 
     f[i].last = static_cast<int*>(c.slot(r.s[4])); f[i].claim = static_cast<int*>(c.slot(r.s[5]));
     f[i].idx = c.slot(r.s[6]); f[i].idx_dtype = r.i[2];
     f[i].vocab = ((int64_t)(uint32_t)r.i[0]) | ((int64_t)r.i[1] << 32); f[i].E = r.i[5];
+    f[i].world = r.i[6]; f[i].rank = r.i[7];
   }
   if (!c.ok) return SWR_ERR_INVALID;
   const float* hyper = static_cast<const float*>(c.slot(h.s[0]));

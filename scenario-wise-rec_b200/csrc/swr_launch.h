@@ -167,6 +167,8 @@ struct LazyField {
   int* last; int* claim;                      // [vocab]
   const void* idx; int idx_dtype;             // index column [B]
   int64_t vocab; int E;
+  int world, rank;                            // world > 1: the table is this rank's shard (row r lives on rank r % world at local row
+                                              // r / world): lookups of other ranks' rows are skipped, idx holds global rows
 };
 int launch_adam_rows(const LazyField* fields, int n_fields, int64_t B, const float* hyper, const int32_t* ctrl, float4* hist, int phase,
                      cudaStream_t st);

@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(256) adam_rows_kernel(const __grid_constant__ 
     if (in) {
       r = load_index(F.idx, F.idx_dtype, i - (int64_t)f * p.B);
       if (r < 0 || r >= F.vocab) r = -1;
+      else if (F.world > 1) r = (r % F.world == F.rank) ? r / F.world : -1;      // only the owner updates a row
     }
     // everything the owner of the row needs is requested at once; a lookup that turns out not to own the row (a
     // duplicate inside the batch) has read one row in vain

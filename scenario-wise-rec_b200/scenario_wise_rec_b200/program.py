@@ -101,6 +101,7 @@ class Program:
     outputs: List[Tuple[int, int, int, int]] = field(default_factory=list)   # plain [B, n] outputs: (raw slot, ld, n, dz slot)
     labels: Dict[int, str] = field(default_factory=dict)
     virtual_fields: list = field(default_factory=list)   # parallel._Field of every row-sharded table the program reads
+    peer_tabs: list = field(default_factory=list)        # (shard parameter, full vocabulary, world) of every table read through peer pointers
     n_launch_fwd: int = 0
     n_launch_bwd: int = 0
 
@@ -851,7 +852,7 @@ class ProgramBuilder:
                        params=self.params, param_arena=self.param_arena, arena_size=dict(self.arena_size),
                        out_slot=self.out_slot, gout_slot=self.gout_slot, oob_slot=self.oob_slot,
                        outputs=[(a.raw, a.ld, a.n, a.dz if a.needs_grad else -1) for a in self._outputs],
-                       labels=dict(self.labels), virtual_fields=list(self.virtual_fields),
+                       labels=dict(self.labels), virtual_fields=list(self.virtual_fields), peer_tabs=list(self.peer_tabs.values()),
                        n_launch_fwd=launches(fwd), n_launch_bwd=launches(bwd))
 
 

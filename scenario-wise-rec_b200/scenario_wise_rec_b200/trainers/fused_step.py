@@ -77,7 +77,7 @@ class FlatArenas:
         # peer path: the shard parameters and their gradients live in memory every rank of the node can address
         self.peer = None
         self.peer_tables = {}
-        if prog.arena_size.get("shard", 0) > 0:
+        if prog.peer_tabs:
             from ..parallel import PeerArena
             self.peer = {"p": PeerArena(self.size["shard"], device), "g": PeerArena(self.size["shard"], device)}
             self.p["shard"], self.g["shard"] = self.peer["p"].tensor, self.peer["g"].tensor
@@ -85,6 +85,23 @@ class FlatArenas:
                 if a == "shard":
                     self.peer_tables[("peers_p", id(p_))] = self.peer["p"].peer_table(o)
                     self.peer_tables[("peers_g", id(p_))] = self.peer["g"].peer_table(o)
+            # sharded tables the program only reads (no gradient reaches them: PPNet's agnostic tables, ppnet.py:54) still
+            # have to be addressable by every rank; they get their own arena, outside the range the optimizer sweeps
+            frozen = [t for t, _v, _w in prog.peer_tabs if ("peers_p", id(t)) not in self.peer_tables]
+            if frozen:
+                total = sum(_align(t.numel(), 4) for t in frozen)
+                self.peer["f"] = PeerArena(max(total, 4), device)
+                o = 0
+                with torch.no_grad():
+                    for t in frozen:
+                        n = t.numel()
+                        view = self.peer["f"].tensor[o:o + n]
+                        view.copy_(t.data.reshape(-1))
+                        t.data = view.view(t.shape)
+                        self.peer_tables[("peers_p", id(t))] = self.peer["f"].peer_table(o)
+                        o += _align(n, 4)
+                import torch.distributed as _dist
+                _dist.barrier()
         self.m = {k: z(k) for k in self.opt_arenas}
         self.v = {k: z(k) for k in self.opt_arenas}
         self.params = []
@@ -118,6 +135,13 @@ class FlatArenas:
         tables = [(p, off, int(p.shape[0]), int(p.shape[1])) for p, a, off, n in entries if a == "emb" and p.dim() == 2]
         if single and tables and os.environ.get("SWR_LAZY_ADAM", "1") != "0" and len(tables) == sum(1 for _p, a, *_ in entries if a == "emb"):
             self.lazy = LazyTables(self, tables)
+        # peer mode: the shard arena is swept densely while that is cheap (cfg2 on 8 GPUs: 87 MB per step) and updated
+        # row-lazily once the sweep would dominate (the 85 M-row item table: 4.8 GB per step and rank)
+        shard_tabs = [(p, off, int(p.shape[0]), int(p.shape[1])) for p, a, off, n in entries if a == "shard" and p.dim() == 2]
+        min_elems = int(float(os.environ.get("SWR_LAZY_SHARD_MIN", "32e6")))
+        if (self.peer is not None and shard_tabs and os.environ.get("SWR_LAZY_ADAM", "1") != "0" and not self.shards
+                and sum(v * e for _p, _o, v, e in shard_tabs) >= min_elems):
+            self.lazy = LazyTables(self, shard_tabs, arena="shard")
 
     def shard_grad(self, shard_param) -> torch.Tensor:
         for p, _a, off, n in self.shards:
@@ -183,10 +207,11 @@ class LazyTables:
 
     HIST_CAP = 1 << 20          # steps of scalars kept on the device (16 B each); a flush re-bases the table
 
-    def __init__(self, flat: "FlatArenas", tables):
+    def __init__(self, flat: "FlatArenas", tables, arena: str = "emb"):
         dev = flat.device
         self.flat = flat
-        self.tables = tables                      # [(param, offset, vocab, E)] inside the emb arena
+        self.arena = arena                        # "emb" (replicated tables, single process) or "shard" (this rank's shards, peer mode)
+        self.tables = tables                      # [(param, offset, rows, E)] inside that arena
         rows = sum(v for _p, _o, v, _e in tables)
         self.row_off = {}
         o = 0
@@ -369,21 +394,35 @@ class FusedTrainStep:
             gscale = 1.0 / dist.get_world_size()
             self._bar = torch.zeros(1, dtype=torch.float32, device=device)
         bce = rec(N.OP_BCE, [self.B, N.DT_F32, RING], [prog.out_slot, X["label"], prog.gout_slot, X["loss"], X["ctrl"]], [gscale])
-        lazy = flat.lazy if (grad_sync is None and self.exchange is None) else None
+        lazy = None
+        if flat.lazy is not None:
+            if flat.lazy.arena == "emb" and grad_sync is None and self.exchange is None and not self.p2p:
+                lazy = flat.lazy
+            elif flat.lazy.arena == "shard" and self.p2p:
+                lazy = flat.lazy
         self.lazy = lazy
-        if lazy is not None:
-            self.g["emb"].zero_()        # invariant of the lazy update: the dense table-gradient arena is all zero between steps
         pre, post = [], []
+        self.g_stage = None
         if lazy is not None:
-            # one sub-record per index column that reads a table of the emb arena (taken from the K2 scatter records)
+            if lazy.arena == "emb":
+                self.g["emb"].zero_()        # invariant of the lazy update: the dense table-gradient arena is all zero between steps
             extra = []          # extra slot pointers appended behind the trainer slots
-            base = {"p": flat.p["emb"].data_ptr(), "g": self.g["emb"].data_ptr(), "m": flat.m["emb"].data_ptr(), "v": flat.v["emb"].data_ptr()}
+            ar = lazy.arena
+            base = {"p": flat.p[ar].data_ptr(), "g": self.g[ar].data_ptr(), "m": flat.m[ar].data_ptr(), "v": flat.v[ar].data_ptr()}
             by_grad_slot = {}
             for p_, (a, off_, n_) in zip(prog.params, prog.param_arena):
-                if a == "emb":
+                if a == ar:
                     for i, d in enumerate(prog.slot_desc):
-                        if d[0] == "grad" and d[1] == "emb" and d[2] == off_:
+                        if d[0] == "grad" and d[1] == ar and d[2] == off_:
                             by_grad_slot[i] = p_
+            # one sub-record per index column that reads a lazily updated table (taken from the K2 scatter records); in
+            # peer mode once per rank: the owner of a row replays / updates it for every rank's lookups, which it sees in
+            # the all-gathered staging buffers
+            world = dist.get_world_size() if self.p2p else 1
+            rank = dist.get_rank() if self.p2p else 0
+            if self.p2p:
+                self.g_stage = torch.zeros(world, self.stage_bytes, dtype=torch.uint8, device=device)
+            input_name = {slot: name for name, slot in prog.inputs.items()}
             subs = []
             recs_b_ = prog.recs_bwd
             i = 0
@@ -393,14 +432,22 @@ class FusedTrainStep:
                     for r in recs_b_[i + 1:i + 1 + ns]:
                         tab = by_grad_slot.get(int(r["s"][0]))
                         if tab is None:
-                            raise RuntimeError("scatter record of a table outside the emb arena")
-                        plist, vocab, E = lazy.field_rec(base, tab, int(r["s"][1]), int(r["i"][2]))
+                            continue             # a table of another arena (small replicated tables in peer mode)
+                        plist, rows_, E = lazy.field_rec(base, tab, int(r["s"][1]), int(r["i"][2]))
                         sl = []
                         for ptr in plist:
                             extra.append(ptr)
                             sl.append(len(ptrs) + len(extra) - 1)
-                        sub = rec(N.OP_GROUP, [*split(vocab), int(r["i"][2]), 0, 0, E], sl + [int(r["s"][1])])
-                        subs.append(sub)
+                        vocab_full = (int(r["i"][0]) & 0xFFFFFFFF) | (int(r["i"][1]) << 32)
+                        for q in range(world):
+                            if self.p2p:         # rank q's copy of the index column inside the gathered staging buffers
+                                extra.append(self.g_stage[q].data_ptr() + self.layout[input_name[int(r["s"][1])]][0])
+                                idx_slot = len(ptrs) + len(extra) - 1
+                            else:
+                                idx_slot = int(r["s"][1])
+                            sub = rec(N.OP_GROUP, [*split(vocab_full if self.p2p else rows_), int(r["i"][2]), 0, 0, E, world if self.p2p else 0, rank],
+                                      sl + [idx_slot])
+                            subs.append(sub)
                 i += 1 + ns
             hist_slot = len(ptrs) + len(extra)
             extra.append(lazy.hist.data_ptr())
@@ -412,25 +459,32 @@ class FusedTrainStep:
             pre = [hdr(0)] + subs
             post = [hdr(1)] + subs
             pre[0]["n_sub"] = post[0]["n_sub"] = len(subs)
-            # flush: every distinct table once
+            # flush: every distinct table once, over its local rows
             fsubs, seen = [], set()
+            rows_of = {base["p"] + 4 * off: v for _p, off, v, _e in lazy.tables}
             for sub in subs:
                 key = int(ptrs[int(sub["s"][0])])
                 if key not in seen:
                     seen.add(key)
-                    fsubs.append(sub)
+                    fs_ = sub.copy()
+                    fs_["i"][0], fs_["i"][1] = split(rows_of[key])
+                    fs_["i"][6] = 0
+                    fsubs.append(fs_)
             fh = rec(N.OP_ADAM_FLUSH, [self.B, 0], [X["hyper"], X["ctrl"], hist_slot])
             fh["n_sub"] = len(fsubs)
             self._flush_recs = stack_ = np.stack([fh] + fsubs).astype(N.REC_DTYPE)
             flat.flush_fn = self._flush_lazy
         # peer mode: a shard's gradient is written by every rank, so it is zeroed by its own Adam sweep (zero_grad flag)
         # at the end of the step, before the barrier that opens the next one -- not in the middle of this one
+        lazy_arena = lazy.arena if lazy is not None else None
         zeros = [rec(N.OP_ZERO, split(4 * gsize[a]), [self.arena_slots[a][1]]) for a in flat.size
-                 if not (lazy is not None and a == "emb") and not (self.p2p and a == "shard")]
+                 if a != lazy_arena and not (self.p2p and a == "shard")]
         adams = [rec(N.OP_ADAM, [*split(flat.size[a]), 1 if (self.p2p and a == "shard") else 0], [*self.arena_slots[a], X["hyper"]])
-                 for a in flat.opt_arenas if (flat.size[a] > 4 or a == "dense") and not (lazy is not None and a == "emb")]
+                 for a in flat.opt_arenas if (flat.size[a] > 4 or a == "dense") and a != lazy_arena]
         stack = lambda lst: np.stack(lst).astype(N.REC_DTYPE)      # noqa: E731
-        parts = ([stack(pre)] if pre else []) + [prog.recs_fwd, stack([bce] + zeros), prog.recs_bwd]
+        # peer mode: the catch-up runs between the all-gather of the index columns and the barrier that opens the gather
+        self.recs_pre = stack(pre) if (pre and self.p2p) else None
+        parts = ([stack(pre)] if (pre and not self.p2p) else []) + [prog.recs_fwd, stack([bce] + zeros), prog.recs_bwd]
         self.recs_a = np.concatenate(parts)
         self.recs_b = stack(adams + post)
         if grad_sync is None and self.exchange is None and not self.p2p:
@@ -445,8 +499,8 @@ class FusedTrainStep:
                 if p_ is f.virt:
                     gv = self.g["virt"][off_:off_ + n_].view(f.virt.shape)
             self._vf.append((f, idx, gv, flat.shard_grad(f.shard) if f.shard.requires_grad else None))
-        self.n_launch = (sum(1 for r in self.recs_a if int(r["kind"]) != N.OP_GROUP) +
-                         (0 if self.recs_b is None else len(self.recs_b)))
+        count = lambda recs: 0 if recs is None else sum(1 for r in recs if int(r["kind"]) != N.OP_GROUP)      # noqa: E731
+        self.n_launch = count(self.recs_a) + count(self.recs_b) + count(self.recs_pre)
         self.graph = None
         self.use_graph = use_graph
         self._warm = 0
@@ -520,8 +574,13 @@ class FusedTrainStep:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         import torch.distributed as dist
         if self.p2p:
-            # every owner has finished the previous step's Adam sweep (and zeroed its shard gradient) before any rank
-            # reads or adds rows in it
+            if self.recs_pre is not None:
+                # row-lazy shards: every rank sees every rank's index columns; the owner of a row replays its postponed
+                # updates before anybody reads it
+                dist.all_gather_into_tensor(self.g_stage.view(-1), self.dev_stage)
+                N.program_run(self.recs_pre, self.ptrs, stream)
+            # every owner has finished the previous step's optimizer work on its shards (and this step's catch-up) before
+            # any rank reads or adds rows in them
             dist.all_reduce(self._bar, op=dist.ReduceOp.SUM)
         for f, idx, _gv, _gs in self._vf:              # embedding exchange, forward half (NCCL over NVLink)
             self.exchange.lookup(f, idx)
