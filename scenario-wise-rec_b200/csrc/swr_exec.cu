@@ -319,6 +319,50 @@ static int run_bmv(const swr_rec_t& h, const swr_rec_t* subs, bool bwd, Ctx& c, 
   return bwd ? launch_bmv_bwd(m, st) : launch_bmv_fwd(m, st);
 }
 
+// ---- side stream --------------------------------------------------------------------------------------------
+// Ops whose results nothing later in the same program reads -- the weight gradients (consumed by the optimizer, after
+// the program) and the running-statistics update of BatchNorm -- are enqueued on a second stream that forks from the
+// caller's stream at the op and joins it again at the end of the program, so the latency-bound narrow layers of the
+// data-gradient chain and their weight gradients overlap.  Under stream capture the fork / join events become graph
+// edges.  SWR_SIDE_STREAM=0 keeps everything on the caller's stream.
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int dev = -1;
+  bool dirty = false;
+  bool ready() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) return false;
+    if (s && d == dev) return true;
+    if (s) { cudaStreamDestroy(s); cudaEventDestroy(fork); cudaEventDestroy(join); s = nullptr; }
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { s = nullptr; return false; }
+    if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess) { cudaStreamDestroy(s); s = nullptr; return false; }
+    dev = d;
+    return true;
+  }
+  // the side stream picks up everything enqueued on `st` so far
+  cudaStream_t enter(cudaStream_t st) {
+    if (cudaEventRecord(fork, st) != cudaSuccess || cudaStreamWaitEvent(s, fork, 0) != cudaSuccess) { cudaGetLastError(); return st; }
+    dirty = true;
+    return s;
+  }
+  int leave(cudaStream_t st) {
+    if (!dirty) return SWR_OK;
+    dirty = false;
+    if (cudaEventRecord(join, s) != cudaSuccess || cudaStreamWaitEvent(st, join, 0) != cudaSuccess) {
+      set_error("side stream join failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return SWR_ERR_CUDA;
+    }
+    return SWR_OK;
+  }
+};
+static thread_local SideStream g_side;
+static bool side_enabled() {
+  static const bool on = [] { const char* e = getenv("SWR_SIDE_STREAM"); return e ? atoi(e) != 0 : true; }();
+  return on;
+}
+
 }  // namespace swr
 
 using namespace swr;
@@ -363,10 +407,7 @@ SWR_API int swr_embedding_scatter_bwd(const float* grad_out, int64_t ld_grad, in
   return launch_scatter(s, static_cast<cudaStream_t>(stream));
 }
 
-SWR_API int swr_program_run(const swr_rec_t* recs, int32_t n_recs, void* const* slots, int32_t n_slots, void* stream) {
-  g_err[0] = 0;
-  if (!recs || n_recs < 0 || !slots) { set_error("program: bad argument"); return SWR_ERR_INVALID; }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+static int program_run_impl(const swr_rec_t* recs, int32_t n_recs, void* const* slots, int32_t n_slots, cudaStream_t main_st, SideStream* side) {
   Ctx c{slots, n_slots, true};
   int i = 0;
   while (i < n_recs) {
@@ -378,6 +419,8 @@ SWR_API int swr_program_run(const swr_rec_t* recs, int32_t n_recs, void* const* 
     int rc = SWR_OK;
     ProfEntry pe{h.kind, i, nullptr, nullptr};
     const bool prof = g_prof_on.load(std::memory_order_relaxed);
+    cudaStream_t st = main_st;
+    if (side && !prof && (h.kind == SWR_OP_FC_WGRAD || h.kind == SWR_OP_BN_UPDATE)) st = side->enter(main_st);
     if (prof) {
       if (cudaEventCreate(&pe.e0) != cudaSuccess || cudaEventCreate(&pe.e1) != cudaSuccess) { set_error("profile: cudaEventCreate failed"); return SWR_ERR_CUDA; }
       cudaEventRecord(pe.e0, st);
@@ -435,6 +478,16 @@ SWR_API int swr_program_run(const swr_rec_t* recs, int32_t n_recs, void* const* 
     i += 1 + h.n_sub;
   }
   return SWR_OK;
+}
+
+SWR_API int swr_program_run(const swr_rec_t* recs, int32_t n_recs, void* const* slots, int32_t n_slots, void* stream) {
+  g_err[0] = 0;
+  if (!recs || n_recs < 0 || !slots) { set_error("program: bad argument"); return SWR_ERR_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SideStream* side = (side_enabled() && g_side.ready()) ? &g_side : nullptr;
+  const int rc = program_run_impl(recs, n_recs, slots, n_slots, st, side);
+  const int rj = side ? side->leave(st) : SWR_OK;      // joined on every path: a capture must not end with a forked stream
+  return rc ? rc : rj;
 }
 
 SWR_API int swr_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream) {

@@ -30,6 +30,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
+#include <algorithm>
 
 namespace swr {
 using namespace tc;
@@ -38,12 +40,19 @@ constexpr int T2_BM = 128;                 // accumulator rows (TMEM lanes) per 
 constexpr int T2_NSTAGER = 8;              // warps 0..7
 constexpr int T2_NEPI = 8;                 // warps 8..15
 constexpr int T2_W_TMA = 16, T2_W_MMA = 17;
-constexpr int T2_THREADS = 18 * 32;
+constexpr int T2_THREADS = 20 * 32;        // five warpgroups: stagers (warps 0-3, 4-7), epilogue (8-11, 12-15), {TMA, MMA, two idle warps}
+// Register budget per thread after the role split (setmaxnreg works on whole warpgroups).  The kernel starts with
+// 96 registers x 640 threads = 61440; the epilogue warps, which keep a 64-column strip of the accumulator tile in
+// registers across the flushes, take what the stagers and the two issuing warps give back:
+// 2 x 128 x 80 + 128 x 48 + 2 x 128 x 136 = 61440 <= 61440.
+constexpr int T2_REG_STAGER = 80, T2_REG_ISSUE = 48, T2_REG_EPI = 136;
 constexpr int T2_MAX_STAGES = 4;
 constexpr int T2_ASTAGES = 4;              // TMEM operand stages
 constexpr uint32_t T2_ACC_COLS = 128;      // columns per accumulator buffer; buffers at TMEM columns 0 and 128
 constexpr uint32_t T2_A_COL0 = 256;        // TMEM-resident operand: stage s at columns 256 + 64 s (32 hi + 32 lo)
 constexpr uint32_t T2_TMEM_COLS = 512;
+constexpr int T2_MAX_CTAS = 191;           // upper bound of the persistent grid (one CTA per SM)
+constexpr int T2_MAX_PERM = 1024;          // launches with more tiles keep contiguous ranges
 constexpr int T2_RAW_BYTES = T2_BM * 128;  // one raw fp32 tile: 128 rows x 32 contraction elements (or 32 batch rows x 128 features)
 constexpr int T2_OT_LD = 36;               // epilogue transpose tile of one epilogue group: 128 rows x 32 columns (+4 pad)
 constexpr int T2_OT_GROUP = T2_BM * T2_OT_LD;       // floats per group
@@ -73,8 +82,13 @@ struct alignas(64) Tc2Params {
   int splits, rows_per_split;      // wgrad
   int cluster;                     // fwd / dgrad: CTAs per cluster (1, 2 or 4) that share every weight tile by TMA multicast;
                                    // a tile index then names `cluster` consecutive row tiles, one per CTA rank
+  unsigned short cta_tile[T2_MAX_CTAS + 1];   // balanced != 0: CTA (cluster) b walks positions [cta_tile[b], cta_tile[b + 1])
+  unsigned short perm[T2_MAX_PERM];           // balanced == 2: position -> tile (tiles of mixed cost dealt out longest first)
+  int balanced;
   long long* dbg;                  // development aid (SWR_TC_DEBUG): clock64 stamps of CTA 0, [role][128]; null in production
 };
+
+static_assert(sizeof(Tc2Params) <= 32764, "kernel parameters are limited to 32764 bytes");
 
 // development aid: event `i` of role `role` (0 TMA, 1 MMA, 2 stager warp 0, 3 epilogue warp 8) of CTA 0
 #define T2_STAMP(role, i) do { if (p.dbg && blockIdx.x == 0 && (i) < 128) p.dbg[(role) * 128 + (i)] = clock64(); } while (0)
@@ -115,6 +129,7 @@ struct T2Tile {
 template <int MODE>
 __device__ __forceinline__ T2Tile t2_decode(const Tc2Params& p, int t, int rank) {
   T2Tile T{};
+  if (p.balanced == 2) t = p.perm[t];
   if (MODE == T2_FWD) {
     int g = 0;
     while (g + 1 < p.n_groups && p.tile_start[g + 1] <= t) ++g;
@@ -168,8 +183,9 @@ __device__ __forceinline__ void t2_setup(Tc2Shared& sh, int tid, int warp, int s
   fence_after_sync();
 }
 
-__device__ __forceinline__ void t2_range(int n_tiles, int cluster, int& t_begin, int& t_end) {
+__device__ __forceinline__ void t2_range(const Tc2Params& p, int n_tiles, int cluster, int& t_begin, int& t_end) {
   const int nb = (int)gridDim.x / cluster, b = (int)blockIdx.x / cluster;
+  if (p.balanced) { t_begin = p.cta_tile[b]; t_end = p.cta_tile[b + 1]; return; }
   const int per = n_tiles / nb, rem = n_tiles % nb;
   t_begin = b * per + min(b, rem);
   t_end = t_begin + per + (b < rem ? 1 : 0);
@@ -216,20 +232,19 @@ __device__ __forceinline__ void t2_lds_row16(const uint8_t* tile, int row, int k
 }
 
 // ---- epilogue helpers -------------------------------------------------------------------------------------
-// drain this warp's share (lane quarter q, columns [64 ch, 64 ch + 64) of an NT-wide accumulator) and add it to acc.
-// Eight columns per load: the running sums already take 64 registers of a 96-register budget, and a spilled register
-// costs an L2 round trip here (the shared-memory carve-out leaves no L1).
+// drain this warp's share (lane quarter q, columns [64 ch, 64 ch + 64) of an NT-wide accumulator) and add it to acc:
+// sixteen columns per tcgen05.ld (the epilogue warpgroups run with T2_REG_EPI registers per thread).
 __device__ __forceinline__ void t2_drain_add(uint32_t tmem_acc, int q, int ch, int NT, float (&acc)[64]) {
   const int my = min(max(NT - 64 * ch, 0), 64);       // 0, 16, 32, 48 or 64 columns (warp-uniform)
   const uint32_t taddr = tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)(64 * ch);
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    if (8 * c < my) {
-      uint32_t r[8];
-      tmem_ld8(taddr + 8 * c, r);
+  for (int c = 0; c < 4; ++c) {
+    if (16 * c < my) {
+      uint32_t r[16];
+      tmem_ld16(taddr + 16 * c, r);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[8 * c + i] += __uint_as_float(r[i]);
+      for (int i = 0; i < 16; ++i) acc[16 * c + i] += __uint_as_float(r[i]);
     }
   }
 }
@@ -242,6 +257,15 @@ __device__ __forceinline__ void t2_acc_to_smem(uint32_t ot_s, int row, int sp, i
                                : make_float4(acc[32 + 4 * i], acc[32 + 4 * i + 1], acc[32 + 4 * i + 2], acc[32 + 4 * i + 3]);
       sts128(ot_s + (uint32_t)(row * T2_OT_LD + 4 * i) * 4u, v);
     }
+}
+// bias + bias2 of output columns [n, n + 4) that lie below n_end (zero elsewhere)
+__device__ __forceinline__ float4 t2_bias_quad(const FcGroup& G, int n, int n_end) {
+  float4 b = t2_zero4();
+  if (n < n_end) b.x = ld_opt(G.bias, n, 0.f) + ld_opt(G.bias2, n, 0.f);
+  if (n + 1 < n_end) b.y = ld_opt(G.bias, n + 1, 0.f) + ld_opt(G.bias2, n + 1, 0.f);
+  if (n + 2 < n_end) b.z = ld_opt(G.bias, n + 2, 0.f) + ld_opt(G.bias2, n + 2, 0.f);
+  if (n + 3 < n_end) b.w = ld_opt(G.bias, n + 3, 0.f) + ld_opt(G.bias2, n + 3, 0.f);
+  return b;
 }
 // forward epilogue value of one accumulator element: bias, optional activation of layers without a norm (GateNU)
 __device__ __forceinline__ float t2_epi_val(float a, float bias, int e_act, float e_scale) {
@@ -264,13 +288,16 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
   const int SB = p.sb, SR = p.sr, F = p.flush, M = p.B;
   int t_begin, t_end;
   const int C = p.cluster, crank = C > 1 ? (int)cluster_ctarank() : 0;
-  t2_range(p.n_tiles, C, t_begin, t_end);
+  t2_range(p, p.n_tiles, C, t_begin, t_end);
   if (tid == 0) T2_STAMP(0, 126);
   t2_setup(sh, tid, warp, T2_NSTAGER / 2, C);
   const uint32_t tmem = sh.tmem_base;
   if (tid == 0) T2_STAMP(0, 127);
 
-  if (warp == T2_W_TMA) {
+  // every role branch opens with its warpgroup's setmaxnreg, so that ptxas allocates the branch under that budget
+  if (warp >= T2_NSTAGER + T2_NEPI) {
+   reg_dec<T2_REG_ISSUE>();
+   if (warp == T2_W_TMA) {
     // ===== TMA producer: weight tiles (ring B) and raw activation-side tiles (ring R) =====
     // The whole warp walks the loop (so every operand is warp-uniform); one elected lane issues.  The two rings
     // advance independently: raw tiles feed the longer chain (stagers -> TMEM -> MMA) and run ahead as far as their
@@ -335,7 +362,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
         advance(cb, SB);
       }
     }
-  } else if (warp == T2_W_MMA) {
+   } else if (warp == T2_W_MMA) {
     // ===== MMA issuer: converged warp, one elected lane issues the tcgen05.mma / commit instructions =====
     {
       T2Ring rb, ra; rb.init(); ra.init();
@@ -366,7 +393,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
         }
       }
     }
+   }
   } else if (warp < T2_NSTAGER) {
+    reg_dec<T2_REG_STAGER>();
     // ===== stagers: raw tile (shared memory) -> transform -> split -> TMEM =====
     // Two groups of four warps (one warp per TMEM lane quarter) alternate over the k-blocks of the CTA, so that the
     // handshake latencies of consecutive k-blocks overlap; a thread stages the 32 contraction elements of its row.
@@ -486,73 +515,108 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
       }
       kbg += T.nkb;
     }
-  } else if (warp < T2_NSTAGER + T2_NEPI) {
+  } else {
+    reg_inc<T2_REG_EPI>();
     // ===== epilogue warps =====
     // Two independent groups of four warps (one per TMEM lane quarter): group ch owns accumulator columns
     // [64 ch, 64 ch + 64), drains them into registers flush by flush, then finishes them in two 32-column passes
-    // through its own transpose tile (so the registers of a pass are dead before its row loop runs).
+    // through its own transpose tile.  What a pass needs from global memory (the destination's raw values in the data
+    // gradient, the bias in the forward) is requested before the accumulators are waited for, so that its latency
+    // hides behind the MMAs / the previous pass.
     const int e = warp - T2_NSTAGER, q = warp & 3, ch = e >> 2;
     uint32_t acc_it = 0;
+    int ev = 0;
     for (int t = t_begin; t < t_end; ++t) {
       float acc[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+      float4 pre[8];     // what a pass needs from global memory: raw rows of the destination (dgrad) / pre[0] = bias quad (fwd)
       {
-        // Only what the drain loop needs is decoded here: the running sums take 64 of the 96 registers, and a spilled
-        // register is an L2 round trip (the shared-memory carve-out leaves no L1).  The tile is decoded again below.
+        // Only what the drain loop needs is decoded here (the tile is decoded again below): the running sums take 64
+        // registers, and everything else that lives across the loop pushes them into local memory.
         const T2Tile T0 = t2_decode<MODE>(p, t, crank);
         if (MODE == T2_DGRAD) {
           // coefficients of the destination's own norm / activation: [4][NT] mu, s, b, r
           const ActDev& D0 = p.g[T0.g].A;
           const bool plain0 = D0.norm.mode == SWR_NORM_NONE && D0.act == SWR_ACT_NONE;
           const int Nend0 = min(D0.n, T0.n0 + T0.NT);
-          float* ccs0 = reinterpret_cast<float*>(smem + p.off_ccs);
-          named_bar(T2_BAR_EPI, 32 * T2_NEPI);
+          float* ccs = reinterpret_cast<float*>(smem + p.off_ccs);
+          named_bar(T2_BAR_EPI, 32 * T2_NEPI);          // every epilogue warp is done with the previous tile's table
           for (int c = tid - 32 * T2_NSTAGER; c < T0.NT; c += 32 * T2_NEPI) {
             ColCoef cc = {0.f, 1.f, 0.f, 1.f};
             if (!plain0 && T0.n0 + c < Nend0) cc = col_coef(D0.norm, T0.n0 + c, p.inv_count);
-            ccs0[c] = cc.mu; ccs0[T0.NT + c] = cc.s; ccs0[2 * T0.NT + c] = cc.b; ccs0[3 * T0.NT + c] = cc.r;
+            ccs[c] = cc.mu; ccs[T0.NT + c] = cc.s; ccs[2 * T0.NT + c] = cc.b; ccs[3 * T0.NT + c] = cc.r;
           }
           named_bar(T2_BAR_EPI, 32 * T2_NEPI);
+        } else {
+          pre[0] = t2_bias_quad(p.g[T0.g], T0.n0 + 64 * ch + (lane & 7) * 4, min(p.g[T0.g].Y.n, T0.n0 + T0.NT));     // pass 0 of this group
         }
         const int NT0 = T0.NT, nflush = (T0.nkb + F - 1) / F;
         for (int f = 0; f < nflush; ++f, ++acc_it) {
           const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
           mbar_wait(&sh.acc_full[buf], aph);
           fence_after_sync();
+          if (tid == 32 * T2_NSTAGER) { T2_STAMP(3, ev); ++ev; }
           t2_drain_add(tmem + buf * T2_ACC_COLS, q, ch, NT0, acc);
           fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&sh.acc_empty[buf]);
         }
       }
+      if (tid == 32 * T2_NSTAGER) { T2_STAMP(3, ev); ++ev; }
       int t_again = t;
       asm volatile("" : "+r"(t_again));              // keeps the decode below from being carried through the drain loop
       const T2Tile T = t2_decode<MODE>(p, t_again, crank);
+      const int gtid = (tid - 32 * T2_NSTAGER) & 127;
+      const int arow = 32 * q + lane;                  // accumulator row this thread drains
+      const int rsub = lane >> 3, c4 = (lane & 7) * 4;  // coalesced pass: 8 lanes per row, 4 rows per warp step
+      const int bar_g = T2_BAR_EGRP + ch;
+      const int row_base = 32 * q + rsub;              // this lane's rows: row_base + 4 i
+      float* ot = reinterpret_cast<float*>(smem + p.off_ot) + ch * T2_OT_GROUP;
+      const uint32_t ot_s = smem_s + (uint32_t)p.off_ot + (uint32_t)(ch * T2_OT_GROUP) * 4u;
+      float* red = reinterpret_cast<float*>(smem + p.off_red) + ch * T2_RED_GROUP;     // [2][4 warps][32]
+      float* ccs = reinterpret_cast<float*>(smem + p.off_ccs);
+      const uint32_t my_ot = ot_s + (uint32_t)(row_base * T2_OT_LD + c4) * 4u;         // + i * 4 rows
       const FcGroup& G = p.g[T.g];
       const ActDev& D = G.A;                          // dgrad: the destination
       const int Nfull = (MODE == T2_FWD) ? G.Y.n : D.n;
       const int Nend = min(Nfull, T.n0 + T.NT);
       const bool has_norm = (MODE == T2_DGRAD) && D.norm.mode != SWR_NORM_NONE;
       const bool plainD = (MODE != T2_DGRAD) || (!has_norm && D.act == SWR_ACT_NONE);
-      const int gtid = (tid - 32 * T2_NSTAGER) & 127;
-      const int arow = 32 * q + lane;                  // accumulator row this thread drains
-      const int rsub = lane >> 3, c4 = (lane & 7) * 4;  // coalesced pass: 8 lanes per row, 4 rows per warp step
-      const int bar_g = T2_BAR_EGRP + ch;
-      float* ot = reinterpret_cast<float*>(smem + p.off_ot) + ch * T2_OT_GROUP;
-      const uint32_t ot_s = smem_s + (uint32_t)p.off_ot + (uint32_t)(ch * T2_OT_GROUP) * 4u;
-      float* red = reinterpret_cast<float*>(smem + p.off_red) + ch * T2_RED_GROUP;     // [2][4 warps][32]
-      float* ccs = reinterpret_cast<float*>(smem + p.off_ccs);
+      const bool atomic_dst = (MODE == T2_DGRAD) && ((p.dst_atomic >> T.d) & 1u);
+      const bool accumulate = (MODE == T2_DGRAD) && (G.flags & FC_A_ACCUMULATE) != 0;
+      const int cnt_rows = min(T2_BM, M - T.m0);
+      const int rows_here = min((max(cnt_rows - row_base, 0) + 3) >> 2, 8);
+      const int my_passes = min(max(T.NT - 64 * ch, 0) + 31, 64) >> 5;     // 32-column passes of this group (0, 1 or 2)
+      const bool base_al = (MODE == T2_FWD) ? ((G.Y.ld % 4 == 0) && is_al16(G.Y.raw))
+                                            : ((D.ld % 4 == 0) && is_al16(D.dz) && is_al16(D.raw));
+      // Requests of pass sp, issued ahead of its use: the forward's bias quad (pass 0: before the drain loop, above), the
+      // data gradient's raw rows (pass 0: here, eight float4 beside the 64 running sums would not fit the drain loop's
+      // registers; pass 1: behind the row loop of pass 0, hidden by its statistics tail).
+      bool pre_ok = false;
+      auto prefetch = [&](int sp) {
+        pre_ok = false;
+        if (sp >= my_passes) return;
+        const int pc0 = 64 * ch + 32 * sp;
+        const int n = T.n0 + pc0 + c4, nv = Nend - n;
+        if (MODE == T2_FWD) {
+          pre[0] = t2_bias_quad(G, n, Nend);
+        } else if (!plainD && !atomic_dst && nv >= 4 && base_al && (n % 4 == 0)) {
+          const float* src = D.raw + (int64_t)(T.m0 + row_base) * D.ld + n;
+          const int64_t ostep = 4 * (int64_t)D.ld;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i < rows_here) pre[i] = *reinterpret_cast<const float4*>(src + i * ostep);
+          pre_ok = true;
+        }
+      };
+      if (MODE == T2_DGRAD) prefetch(0);
       // ---- final epilogue of this group's columns, 32 per pass ----
       // Column statistics stay in fp32 until one thread per column widens them (fp64 throughput is a small fraction
       // of fp32's): forward moments are sums of deviations from the tile's first row, a centre every thread can read.
-      const int cnt_rows = min(T2_BM, M - T.m0);
-      const int row_base = 32 * q + rsub;            // this lane's rows: row_base + 4 i
-      const int rows_here = min((max(cnt_rows - row_base, 0) + 3) >> 2, 8);
 #pragma unroll 1
-      for (int sp = 0; sp < 2; ++sp) {
+      for (int sp = 0; sp < my_passes; ++sp) {
         const int pc0 = 64 * ch + 32 * sp;
-        if (pc0 >= T.NT) break;                      // uniform over the group
         const int pc = min(32, T.NT - pc0);
         const int nvalid = min(max(Nend - (T.n0 + pc0), 0), pc);
         named_bar(bar_g, 128);                       // the group is done with the previous contents of ot / red
@@ -560,30 +624,27 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
         named_bar(bar_g, 128);
         const int nv = nvalid - c4;                  // valid components of this lane's column quad (<= 0: none)
         const int n = T.n0 + pc0 + c4;               // first output column of the quad
-        const uint32_t my_ot = ot_s + (uint32_t)(row_base * T2_OT_LD + c4) * 4u;   // + i * 4 rows
         float4 s1 = t2_zero4(), s2 = t2_zero4();
         if (MODE == T2_FWD) {
           float* Y = const_cast<float*>(G.Y.raw);
-          const bool vec = (nv >= 4) && (G.Y.ld % 4 == 0) && is_al16(Y) && (n % 4 == 0);
+          const bool vec = (nv >= 4) && base_al && (n % 4 == 0);
+          const float4 bias = pre[0];
           if (nv > 0) {
-            float4 bias;
-            bias.x = ld_opt(G.bias, n, 0.f) + ld_opt(G.bias2, n, 0.f);
-            bias.y = nv > 1 ? ld_opt(G.bias, n + 1, 0.f) + ld_opt(G.bias2, n + 1, 0.f) : 0.f;
-            bias.z = nv > 2 ? ld_opt(G.bias, n + 2, 0.f) + ld_opt(G.bias2, n + 2, 0.f) : 0.f;
-            bias.w = nv > 3 ? ld_opt(G.bias, n + 3, 0.f) + ld_opt(G.bias2, n + 3, 0.f) : 0.f;
             float* dst = Y + (int64_t)(T.m0 + row_base) * G.Y.ld + n;
             const int64_t dstep = 4 * (int64_t)G.Y.ld;
             const float4 r0 = lds128(ot_s + (uint32_t)c4 * 4u);      // row 0 of the tile: always a valid batch row
             if (G.e_act == SWR_ACT_NONE && vec) {   // the common case, branch-free per row
               const float4 y0 = make_float4(r0.x + bias.x, r0.y + bias.y, r0.z + bias.z, r0.w + bias.w);
-      #pragma unroll 2
-              for (int i = 0; i < rows_here; ++i) {
-                const float4 a = lds128(my_ot + (uint32_t)(4 * i * T2_OT_LD) * 4u);
-                const float4 y = make_float4(a.x + bias.x, a.y + bias.y, a.z + bias.z, a.w + bias.w);
-                *reinterpret_cast<float4*>(dst + i * dstep) = y;
-                const float4 d = make_float4(y.x - y0.x, y.y - y0.y, y.z - y0.z, y.w - y0.w);
-                s1.x += d.x; s1.y += d.y; s1.z += d.z; s1.w += d.w;
-                s2.x = fmaf(d.x, d.x, s2.x); s2.y = fmaf(d.y, d.y, s2.y); s2.z = fmaf(d.z, d.z, s2.z); s2.w = fmaf(d.w, d.w, s2.w);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (i < rows_here) {
+                  const float4 a = lds128(my_ot + (uint32_t)(4 * i * T2_OT_LD) * 4u);
+                  const float4 y = make_float4(a.x + bias.x, a.y + bias.y, a.z + bias.z, a.w + bias.w);
+                  *reinterpret_cast<float4*>(dst + i * dstep) = y;
+                  const float4 d = make_float4(y.x - y0.x, y.y - y0.y, y.z - y0.z, y.w - y0.w);
+                  s1.x += d.x; s1.y += d.y; s1.z += d.z; s1.w += d.w;
+                  s2.x = fmaf(d.x, d.x, s2.x); s2.y = fmaf(d.y, d.y, s2.y); s2.z = fmaf(d.z, d.z, s2.z); s2.w = fmaf(d.w, d.w, s2.w);
+                }
               }
             } else {
               const float4 y0 = make_float4(t2_epi_val(r0.x, bias.x, G.e_act, G.e_scale), t2_epi_val(r0.y, bias.y, G.e_act, G.e_scale),
@@ -602,10 +663,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
               }
             }
           }
+          prefetch(sp + 1);
         } else {
-          const bool accumulate = (G.flags & FC_A_ACCUMULATE) != 0;
-          const bool atomic_dst = (p.dst_atomic >> T.d) & 1u;
-          const bool vec = (nv >= 4) && (D.ld % 4 == 0) && is_al16(D.dz) && is_al16(D.raw) && (n % 4 == 0);
+          const bool vec = (nv >= 4) && base_al && (n % 4 == 0);
           if (nv > 0) {
             const int cc0 = pc0 + c4;
             const int64_t o0 = (int64_t)(T.m0 + row_base) * D.ld + n, ostep = 4 * (int64_t)D.ld;
@@ -613,13 +673,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
               const float4 mu = t2_ld4s(ccs + cc0), sc = t2_ld4s(ccs + T.NT + cc0), bb = t2_ld4s(ccs + 2 * T.NT + cc0), rr4 = t2_ld4s(ccs + 3 * T.NT + cc0);
               const float slope = t2_slope(D.act);
               const bool sigD = D.act == SWR_ACT_SIGMOID;
-#pragma unroll 2
-              for (int i = 0; i < rows_here; ++i) {
-                {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (i < rows_here) {
                   float4 dz = lds128(my_ot + (uint32_t)(4 * i * T2_OT_LD) * 4u);
                   float* dst = D.dz + o0 + i * ostep;
                   if (!plainD) {
-                    const float4 raw = *reinterpret_cast<const float4*>(D.raw + o0 + i * ostep);
+                    const float4 raw = pre_ok ? pre[i] : *reinterpret_cast<const float4*>(D.raw + o0 + i * ostep);
                     const float4 xc = make_float4(raw.x - mu.x, raw.y - mu.y, raw.z - mu.z, raw.w - mu.w);
                     const float4 z = make_float4(fmaf(xc.x, sc.x, bb.x), fmaf(xc.y, sc.y, bb.y), fmaf(xc.z, sc.z, bb.z), fmaf(xc.w, sc.w, bb.w));
                     if (sigD) {
@@ -672,6 +732,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
               s1 = make_float4(t1[0], t1[1], t1[2], t1[3]); s2 = make_float4(t2[0], t2[1], t2[2], t2[3]);
             }
           }
+          prefetch(sp + 1);
         }
         const bool want_stats = (MODE == T2_FWD) ? (G.stats_out != nullptr) : (has_norm && D.dstats != nullptr);
         if (want_stats) {           // uniform over the group
@@ -686,8 +747,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
             *reinterpret_cast<float4*>(red + (0 * 4 + q) * 32 + c4) = s1;
             *reinterpret_cast<float4*>(red + (1 * 4 + q) * 32 + c4) = s2;
           }
-            named_bar(bar_g, 128);
-            if (gtid < nvalid && cnt_rows > 0) {      // one thread per column: fp32 sum over the group's warps, widened once
+          named_bar(bar_g, 128);
+          if (gtid < nvalid && cnt_rows > 0) {      // one thread per column: fp32 sum over the group's warps, widened once
             const float S1 = red[gtid] + red[32 + gtid] + red[64 + gtid] + red[96 + gtid];
             const float S2 = red[128 + gtid] + red[160 + gtid] + red[192 + gtid] + red[224 + gtid];
             const int col = T.n0 + pc0 + gtid;
@@ -701,8 +762,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
               atomicAdd(D.dstats + 2 * col + 1, (double)S2);
             }
           }
-            }
+        }
       }
+      if (tid == 32 * T2_NSTAGER) { T2_STAMP(3, ev); ++ev; }
     }
   }
   if (tid == 32 * T2_NSTAGER) T2_STAMP(3, 127);
@@ -745,11 +807,16 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_wgrad_kernel(const __gri
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int SB = p.sb, SR = p.sr, F = p.flush;
   int t_begin, t_end;
-  t2_range(p.n_tiles, 1, t_begin, t_end);
+  t2_range(p, p.n_tiles, 1, t_begin, t_end);
+  if (tid == 0) T2_STAMP(0, 126);
   t2_setup(sh, tid, warp, T2_NSTAGER, 1);
   const uint32_t tmem = sh.tmem_base;
-  if (warp == T2_W_TMA) {
+  if (tid == 0) T2_STAMP(0, 127);
+  if (warp >= T2_NSTAGER + T2_NEPI) {
+   reg_dec<T2_REG_ISSUE>();
+   if (warp == T2_W_TMA) {
     T2Ring rr; rr.init();
+    int ev = 0;
     for (int t = t_begin; t < t_end; ++t) {
       const T2Tile T = t2_decode_wgrad(p, t);
       const FcGroup& G = p.g[T.g];
@@ -766,11 +833,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_wgrad_kernel(const __gri
           tma_load_2d(rdst + 2 * T2_RAW_BYTES, &p.tm2[T.g], T.n0, b0, &sh.full_r[rr.s]);
         }
         __syncwarp();
+        if (lane == 0) { T2_STAMP(0, ev); } ++ev;
       }
     }
-  } else if (warp == T2_W_MMA) {
+   } else if (warp == T2_W_MMA) {
     T2Ring ra; ra.init();
     uint32_t acc_it = 0;
+    int ev = 0;
     for (int t = t_begin; t < t_end; ++t) {
       const T2Tile T = t2_decode_wgrad(p, t);
       const uint32_t b_bytes = (uint32_t)T.NT * 128u;
@@ -790,15 +859,18 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_wgrad_kernel(const __gri
         }
         __syncwarp();
         if (last) { ++acc_it; fpos = 0; } else ++fpos;
+        if (lane == 0) { T2_STAMP(1, ev); } ++ev;
       }
     }
+   }
   } else if (warp < T2_NSTAGER) {
+    reg_dec<T2_REG_STAGER>();
     const int q = warp & 3, kh = warp >> 2, stid = tid;
     const int nl = 32 * q + lane;                    // output feature inside the tile = TMEM lane
     const uint32_t ta = tmem + T2_A_COL0 + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * kh);
     float* coef = reinterpret_cast<float*>(smem + p.off_coef);   // [3][NT]: mu, s, b of the input columns of the tile
     T2Ring rr, ra; rr.init(); ra.init();
-    int cur_g = -1, cur_n0 = -1;
+    int cur_g = -1, cur_n0 = -1, ev = 0;
     for (int t = t_begin; t < t_end; ++t) {
       const T2Tile T = t2_decode_wgrad(p, t);
       if (T.nkb == 0) continue;
@@ -832,6 +904,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_wgrad_kernel(const __gri
       float rowsum = 0.f;
       for (int kb = 0; kb < T.nkb; ++kb, rr.next(SR), ra.next(SB)) {
         mbar_wait(&sh.full_r[rr.s], rr.ph);
+        if (tid == 0) { T2_STAMP(2, ev); ++ev; }
         const float* rt = reinterpret_cast<const float*>(smem + p.off_r + rr.s * p.stage_r);
         // ---- dY^T: 16 batch rows of output feature n ----
         float v[16];
@@ -877,13 +950,15 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_wgrad_kernel(const __gri
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sh.full_a[ra.s]);
+        if (tid == 0) { T2_STAMP(2, ev); ++ev; }
       }
       if (T.n0 == 0 && n_ok) {    // bias gradient: the j-tile 0 CTAs carry it (two threads per output feature)
         if (G.dbias) atomicAdd(G.dbias + n, rowsum);
         if (G.dbias2) atomicAdd(G.dbias2 + n, rowsum);
       }
     }
-  } else if (warp < T2_NSTAGER + T2_NEPI) {
+  } else {
+    reg_inc<T2_REG_EPI>();
     // two independent epilogue groups, see fc_tc2_kernel
     const int e = warp - T2_NSTAGER, q = warp & 3, ch = e >> 2;
     const int arow = 32 * q + lane;
@@ -892,6 +967,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_wgrad_kernel(const __gri
     const float* ot = reinterpret_cast<const float*>(smem + p.off_ot) + ch * T2_OT_GROUP;
     const uint32_t ot_s = smem_s + (uint32_t)p.off_ot + (uint32_t)(ch * T2_OT_GROUP) * 4u;
     uint32_t acc_it = 0;
+    int ev = 0;
     for (int t = t_begin; t < t_end; ++t) {
       const T2Tile T = t2_decode_wgrad(p, t);
       if (T.nkb == 0) continue;
@@ -905,6 +981,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_wgrad_kernel(const __gri
         const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
         mbar_wait(&sh.acc_full[buf], aph);
         fence_after_sync();
+        if (tid == 32 * T2_NSTAGER) { T2_STAMP(3, ev); ++ev; }
         t2_drain_add(tmem + buf * T2_ACC_COLS, q, ch, T.NT, acc);
         fence_before_sync();
         __syncwarp();
@@ -966,8 +1043,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_wgrad_kernel(const __gri
           }
         }
       }
+      if (tid == 32 * T2_NSTAGER) { T2_STAMP(3, ev); ++ev; }
     }
   }
+  if (tid == 32 * T2_NSTAGER) T2_STAMP(3, 127);
+  if (tid == 0) T2_STAMP(2, 127);
   fence_before_sync();
   __syncthreads();
   if (warp == T2_W_MMA) { __syncwarp(); tmem_dealloc(tmem, T2_TMEM_COLS); }
@@ -1162,22 +1242,22 @@ static int t2_pick_cluster(bool all128, int mtiles) {
   while (c > 1 && mtiles < c) c >>= 1;
   return c;
 }
+// CTAs (clusters) of the persistent grid: one per SM, never more than tiles
 template <class K>
-static int t2_launch(K kernel, int n_tiles, int cluster, size_t smem, const Tc2Params& p, cudaStream_t st, const char* name) {
+static int t2_grid(K kernel, int n_tiles, int cluster, size_t smem) {
   const int sms = t2_num_sms();
-  cudaLaunchConfig_t cfg{};
-  cfg.blockDim = dim3(T2_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
   int max_clusters = sms / cluster;
   if (cluster > 1) {
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
     // clusters that can be resident at once (GPC boundaries strand a few SMs at cluster size 4)
     static thread_local int cached[5] = {0, 0, 0, 0, 0};
     if (!cached[cluster]) {
+      cudaLaunchConfig_t cfg{};
+      cfg.blockDim = dim3(T2_THREADS, 1, 1);
+      cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
       cfg.gridDim = dim3(sms / cluster * cluster, 1, 1);
       int n = 0;
       if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = max_clusters; }
@@ -1185,7 +1265,81 @@ static int t2_launch(K kernel, int n_tiles, int cluster, size_t smem, const Tc2P
     }
     max_clusters = min(max_clusters, cached[cluster]);
   }
-  cfg.gridDim = dim3(min(n_tiles, max_clusters) * cluster, 1, 1);
+  return max(1, min(min(n_tiles, max_clusters), T2_MAX_CTAS));
+}
+
+// Contiguous tile ranges of (almost) equal cost: the smallest bottleneck cost `cap` for which a greedy walk needs at most
+// `nb` ranges (binary search), then that walk.  cost[t] > 0.
+static void t2_balance(Tc2Params& p, const std::vector<int>& cost, int nb) {
+  const int n = (int)cost.size();
+  p.balanced = 0;
+  if (n > 65535 || nb > T2_MAX_CTAS || nb <= 0) return;
+  long long lo = 0, hi = 0;
+  for (int c : cost) { lo = std::max<long long>(lo, c); hi += c; }
+  auto ranges_needed = [&](long long cap) {
+    int r = 1; long long cur = 0;
+    for (int c : cost) { if (cur + c > cap) { ++r; cur = 0; } cur += c; }
+    return r;
+  };
+  while (lo < hi) {
+    const long long mid = (lo + hi) / 2;
+    if (ranges_needed(mid) <= nb) hi = mid; else lo = mid + 1;
+  }
+  // tiles of mixed cost (gate tiles beside expert tiles): deal them out longest first to the least loaded CTA and keep
+  // that assignment when its bottleneck beats the contiguous one by a tenth (contiguous ranges change group less often,
+  // and every change rebuilds a coefficient table)
+  if (n <= T2_MAX_PERM && nb > 1) {
+    std::vector<int> order(n);
+    for (int t = 0; t < n; ++t) order[t] = t;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b_) { return cost[a] > cost[b_]; });
+    std::vector<long long> load(nb, 0);
+    std::vector<std::vector<int>> mine(nb);
+    for (int t : order) {
+      int best = 0;
+      for (int c = 1; c < nb; ++c) if (load[c] < load[best]) best = c;
+      load[best] += cost[t]; mine[best].push_back(t);
+    }
+    const long long lpt = *std::max_element(load.begin(), load.end());
+    if (lpt * 10 < lo * 9) {
+      int pos = 0;
+      for (int c = 0; c < nb; ++c) {
+        p.cta_tile[c] = (unsigned short)pos;
+        for (int t : mine[c]) p.perm[pos++] = (unsigned short)t;
+      }
+      p.cta_tile[nb] = (unsigned short)pos;
+      p.balanced = 2;
+      return;
+    }
+  }
+  int b = 0; long long cur = 0;
+  p.cta_tile[0] = 0;
+  for (int t = 0; t < n; ++t) {
+    // start a new range when the cap would be exceeded, or when the tiles left are just enough to give every remaining
+    // CTA one (no CTA stays idle while another holds two tiles)
+    const bool must = (n - t) <= (nb - 1 - b) && cur > 0;
+    if ((cur + cost[t] > lo || must) && b + 1 < nb) { p.cta_tile[++b] = (unsigned short)t; cur = 0; }
+    cur += cost[t];
+  }
+  while (b < nb) p.cta_tile[++b] = (unsigned short)n;
+  p.balanced = 1;
+}
+// modelled cycles of one tile (measured on cfg2, profiles/r02_fc_tc2_notes.md): a k-block costs what the slower of the
+// stagers (~600) and the MMAs (12 x NT / 128 x ~105) takes, the final epilogue ~1500 + 12 NT
+static int t2_tile_cost(int nkb, int nt) { return nkb * std::max(600, 10 * nt) + 1500 + 12 * nt; }
+
+template <class K>
+static int t2_launch(K kernel, int n_ctas, int cluster, size_t smem, const Tc2Params& p, cudaStream_t st, const char* name) {
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(T2_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (cluster > 1) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  cfg.gridDim = dim3(n_ctas * cluster, 1, 1);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
   if (e != cudaSuccess) { set_error("launch of %s failed: %s", name, cudaGetErrorString(e)); return SWR_ERR_CUDA; }
   count_launch();
@@ -1245,6 +1399,34 @@ bool fc_tc2_usable(const FcGroup* groups, int n_groups, int pass) {
   return true;
 }
 
+// development aid (SWR_TC_DEBUG): clock64 stamps of CTA 0 per warp role, printed after the launch
+struct T2Debug {
+  bool on;
+  static long long* buffer() { static long long* d = nullptr; if (!d) cudaMalloc(&d, 512 * sizeof(long long)); return d; }
+  T2Debug(Tc2Params& p, cudaStream_t st) {
+    static const bool debug = getenv("SWR_TC_DEBUG") != nullptr;
+    on = debug;
+    if (on) { cudaMemsetAsync(buffer(), 0, 512 * sizeof(long long), st); p.dbg = buffer(); }
+  }
+  void report(const char* what, const Tc2Params& p, int tiles, cudaStream_t st) const {
+    if (!on) return;
+    long long h[512];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, buffer(), sizeof(h), cudaMemcpyDeviceToHost);
+    const long long t0 = h[126];
+    int t_per = tiles / 148 + (tiles % 148 ? 1 : 0);
+    fprintf(stderr, "[tc2 %s dbg] tiles=%d (cta0: %d) groups=%d K0=%d N0=%d cluster=%d nt0=%d sb=%d sr=%d flush=%d splits=%d setup=%lld\n", what, tiles, t_per,
+            p.n_groups, p.g[0].A.n, p.g[0].Y.n, p.cluster, p.nt[0], p.sb, p.sr, p.flush, p.splits, h[127] - t0);
+    const char* names[4] = {"tma", "mma", "stg", "epi"};
+    for (int r = 0; r < 4; ++r) {
+      fprintf(stderr, "  %s:", names[r]);
+      for (int i = 0; i < 126 && h[r * 128 + i]; ++i) fprintf(stderr, " %lld", h[r * 128 + i] - t0);
+      if (r == 2 || r == 3) fprintf(stderr, " | end %lld", h[r * 128 + 127] - t0);
+      fprintf(stderr, "\n");
+    }
+  }
+};
+
 int launch_fc_tc2_fwd(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st) {
   Tc2Params p{};
   p.n_groups = n_groups; p.B = (int)B; p.inv_count = 1.0f / (float)B;
@@ -1274,29 +1456,18 @@ int launch_fc_tc2_fwd(const FcGroup* groups, int n_groups, int64_t B, cudaStream
   if (rc) return rc;
   rc = t2_set_smem(fc_tc2_kernel<T2_FWD>, smem);
   if (rc) return rc;
-  static const bool debug = getenv("SWR_TC_DEBUG") != nullptr;
-  static long long* dbg_dev = nullptr;
-  if (debug) {
-    if (!dbg_dev) cudaMalloc(&dbg_dev, 512 * sizeof(long long));
-    cudaMemsetAsync(dbg_dev, 0, 512 * sizeof(long long), st);
-    p.dbg = dbg_dev;
+  const int nb = t2_grid(fc_tc2_kernel<T2_FWD>, tiles, C, smem);
+  {
+    std::vector<int> cost;
+    cost.reserve(tiles);
+    for (int g = 0; g < n_groups; ++g)
+      cost.insert(cost.end(), p.tile_start[g + 1] - p.tile_start[g], t2_tile_cost(ceil_div(groups[g].A.n, KBLK), p.nt[g]));
+    t2_balance(p, cost, nb);
   }
-  rc = t2_launch(fc_tc2_kernel<T2_FWD>, tiles, C, smem, p, st, "fc_tc2_kernel<fwd>");
+  T2Debug dbg(p, st);
+  rc = t2_launch(fc_tc2_kernel<T2_FWD>, nb, C, smem, p, st, "fc_tc2_kernel<fwd>");
   if (rc) return rc;
-  if (debug) {
-    long long h[512];
-    cudaStreamSynchronize(st);
-    cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
-    const long long t0 = h[126];
-    fprintf(stderr, "[tc2 fwd dbg] tiles=%d cluster=%d nt0=%d sb=%d sr=%d flush=%d setup=%lld\n", tiles, C, p.nt[0], p.sb, p.sr, p.flush, h[127] - t0);
-    const char* names[4] = {"tma", "mma", "stg", "epi"};
-    for (int r = 0; r < 4; ++r) {
-      fprintf(stderr, "  %s:", names[r]);
-      for (int i = 0; i < 126 && h[r * 128 + i]; ++i) fprintf(stderr, " %lld", h[r * 128 + i] - t0);
-      if (r == 2 || r == 3) fprintf(stderr, " | end %lld", h[r * 128 + 127] - t0);
-      fprintf(stderr, "\n");
-    }
-  }
+  dbg.report("fwd", p, tiles, st);
   return SWR_OK;
 }
 
@@ -1370,7 +1541,19 @@ int launch_fc_tc2_dgrad(const FcGroup* groups, const int* dst_group_in, int n_ds
   if (rc) return rc;
   rc = t2_set_smem(fc_tc2_kernel<T2_DGRAD>, smem);
   if (rc) return rc;
-  return t2_launch(fc_tc2_kernel<T2_DGRAD>, tiles, C, smem, p, st, "fc_tc2_kernel<dgrad>");
+  const int nb = t2_grid(fc_tc2_kernel<T2_DGRAD>, tiles, C, smem);
+  {
+    std::vector<int> cost;
+    cost.reserve(tiles);
+    for (int d = 0; d < n_dst; ++d)
+      cost.insert(cost.end(), p.dst_tile[d + 1] - p.dst_tile[d], t2_tile_cost(p.tile_start[dst_group[d + 1]] - p.tile_start[dst_group[d]], p.nt[d]));
+    t2_balance(p, cost, nb);
+  }
+  T2Debug dbg(p, st);
+  rc = t2_launch(fc_tc2_kernel<T2_DGRAD>, nb, C, smem, p, st, "fc_tc2_kernel<dgrad>");
+  if (rc) return rc;
+  dbg.report("dgrad", p, tiles, st);
+  return SWR_OK;
 }
 
 int launch_fc_tc2_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStream_t st) {
@@ -1393,11 +1576,22 @@ int launch_fc_tc2_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStre
     rc = t2_make_act_map(&p.tm2[g], G.A.raw, (int)B, G.A.n, G.A.ld, p.nt[g], 32, false);
     if (rc) return rc;
   }
-  // split the batch so that the launch has about two tiles per SM; keep >= 4 k-blocks (128 rows) per split
+  // Split the batch so that the modelled duration is smallest: a CTA walks ceil(tiles / SMs) tiles, a tile costs its
+  // k-blocks (the stagers bound the loop: ~2000 cycles each) plus ~8000 cycles of fixed work (coefficient tables,
+  // pipeline fill, drain and the weight-gradient atomics); measured on cfg2 (profiles/r02_fc_tc2_notes.md).
+  // Keep >= 4 k-blocks (128 rows) per split.
   const int sms = t2_num_sms();
-  int splits = max(1, min((2 * sms + base / 2) / max(base, 1), ceil_div(B, 4 * KBLK)));
-  int rows = t2_round_up(ceil_div(B, splits), KBLK);
-  splits = ceil_div(B, rows);
+  int splits = 1, rows = t2_round_up((int)B, KBLK);
+  {
+    long long best = -1;
+    const int smax = max(1, min(ceil_div(B, 4 * KBLK), 64));
+    for (int s_ = 1; s_ <= smax; ++s_) {
+      const int r_ = t2_round_up(ceil_div(B, s_), KBLK), n_ = ceil_div(B, r_);
+      const long long per_cta = ceil_div(base * n_, sms);
+      const long long t_ = per_cta * ((long long)(r_ / KBLK) * 2000 + 8000);
+      if (best < 0 || t_ < best) { best = t_; splits = n_; rows = r_; }
+    }
+  }
   p.splits = splits; p.rows_per_split = rows;
   int tiles = 0;
   for (int g = 0; g < n_groups; ++g) {
@@ -1411,7 +1605,11 @@ int launch_fc_tc2_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStre
   rc = t2_set_smem(fc_tc2_wgrad_kernel, smem);
   if (rc) return rc;
   p.cluster = 1;
-  return t2_launch(fc_tc2_wgrad_kernel, tiles, 1, smem, p, st, "fc_tc2_wgrad_kernel");
+  T2Debug dbg(p, st);
+  rc = t2_launch(fc_tc2_wgrad_kernel, t2_grid(fc_tc2_wgrad_kernel, tiles, 1, smem), 1, smem, p, st, "fc_tc2_wgrad_kernel");
+  if (rc) return rc;
+  dbg.report("wgrad", p, tiles, st);
+  return SWR_OK;
 }
 
 }  // namespace swr

@@ -1,5 +1,5 @@
 """Development aid: one eager training step of a BASELINE case with SWR_TC_DEBUG=1 (per-role clock stamps of CTA 0 of
-every tcgen05 forward launch go to stderr)."""
+every tcgen05 forward / data-gradient / weight-gradient launch go to stderr)."""
 import os, sys
 os.environ.setdefault("SWR_TC_DEBUG", "1")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -16,4 +16,7 @@ xg = {k: v.to("cuda:0") for k, v in x.items()}
 for i in range(3):
     sys.stderr.write(f"--- pass {i}\n")
     out = model(xg)
+    torch.cuda.synchronize()
+    sys.stderr.write(f"--- backward {i}\n")
+    out.sum().backward()
     torch.cuda.synchronize()
