@@ -358,10 +358,12 @@ struct SideStream {
   }
 };
 static thread_local SideStream g_side;
-static bool side_enabled() {
-  static const bool on = [] { const char* e = getenv("SWR_SIDE_STREAM"); return e ? atoi(e) != 0 : true; }();
-  return on;
+// bit 0: weight gradients, bit 1: BatchNorm running-statistics update
+static int side_mask() {
+  static const int m = [] { const char* e = getenv("SWR_SIDE_STREAM"); return e ? atoi(e) : 3; }();
+  return m;
 }
+static bool side_enabled() { return side_mask() != 0; }
 
 }  // namespace swr
 
@@ -420,7 +422,7 @@ static int program_run_impl(const swr_rec_t* recs, int32_t n_recs, void* const* 
     ProfEntry pe{h.kind, i, nullptr, nullptr};
     const bool prof = g_prof_on.load(std::memory_order_relaxed);
     cudaStream_t st = main_st;
-    if (side && !prof && (h.kind == SWR_OP_FC_WGRAD || h.kind == SWR_OP_BN_UPDATE)) st = side->enter(main_st);
+    if (side && !prof && ((h.kind == SWR_OP_FC_WGRAD && (side_mask() & 1)) || (h.kind == SWR_OP_BN_UPDATE && (side_mask() & 2)))) st = side->enter(main_st);
     if (prof) {
       if (cudaEventCreate(&pe.e0) != cudaSuccess || cudaEventCreate(&pe.e1) != cudaSuccess) { set_error("profile: cudaEventCreate failed"); return SWR_ERR_CUDA; }
       cudaEventRecord(pe.e0, st);

@@ -46,6 +46,9 @@ constexpr int T2_THREADS = 20 * 32;        // five warpgroups: stagers (warps 0-
 // registers across the flushes, take what the stagers and the two issuing warps give back:
 // 2 x 128 x 80 + 128 x 48 + 2 x 128 x 136 = 61440 <= 61440.
 constexpr int T2_REG_STAGER = 80, T2_REG_ISSUE = 48, T2_REG_EPI = 136;
+// weight gradient: its stagers do more per k-block (both operands) and its epilogue keeps no prefetched rows:
+// 2 x 128 x 96 + 128 x 48 + 2 x 128 x 112 = 59392
+constexpr int T2W_REG_STAGER = 96, T2W_REG_EPI = 112;
 constexpr int T2_MAX_STAGES = 4;
 constexpr int T2_ASTAGES = 4;              // TMEM operand stages
 constexpr uint32_t T2_ACC_COLS = 128;      // columns per accumulator buffer; buffers at TMEM columns 0 and 128
@@ -93,6 +96,18 @@ static_assert(sizeof(Tc2Params) <= 32764, "kernel parameters are limited to 3276
 // development aid: event `i` of role `role` (0 TMA, 1 MMA, 2 stager warp 0, 3 epilogue warp 8) of CTA 0
 #define T2_STAMP(role, i) do { if (p.dbg && blockIdx.x == 0 && (i) < 128) p.dbg[(role) * 128 + (i)] = clock64(); } while (0)
 
+struct T2Tile {
+  int g;            // fwd / wgrad: group;  dgrad: first group of the destination
+  int ge;           // dgrad: one past the last group of the destination
+  int d;            // dgrad: destination entry
+  int m0, n0;       // first accumulator row (batch row; wgrad: output feature) / column of the tile
+  int NT;           // accumulator columns
+  int nkb;          // k-blocks of 32 contraction elements
+  int kb0;          // dgrad: first k-block of the destination in the launch-wide numbering
+  int b_begin, b_end;   // wgrad: batch rows of this split
+};
+
+
 struct Tc2Shared {
   uint64_t full_b[T2_MAX_STAGES];  // fwd/dgrad: TMA landed the weight tile
   uint64_t empty_b[T2_MAX_STAGES]; // tcgen05.commit: the MMAs that read the stage are done
@@ -115,16 +130,6 @@ struct T2Ring {                    // position in a ring of mbarrier-guarded sta
   __device__ __forceinline__ void next(int S) { if (++s == S) { s = 0; ph ^= 1u; } }
 };
 
-struct T2Tile {
-  int g;            // fwd / wgrad: group;  dgrad: first group of the destination
-  int ge;           // dgrad: one past the last group of the destination
-  int d;            // dgrad: destination entry
-  int m0, n0;       // first accumulator row (batch row; wgrad: output feature) / column of the tile
-  int NT;           // accumulator columns
-  int nkb;          // k-blocks of 32 contraction elements
-  int kb0;          // dgrad: first k-block of the destination in the launch-wide numbering
-  int b_begin, b_end;   // wgrad: batch rows of this split
-};
 
 template <int MODE>
 __device__ __forceinline__ T2Tile t2_decode(const Tc2Params& p, int t, int rank) {
@@ -290,6 +295,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
   const int C = p.cluster, crank = C > 1 ? (int)cluster_ctarank() : 0;
   t2_range(p, p.n_tiles, C, t_begin, t_end);
   if (tid == 0) T2_STAMP(0, 126);
+  if (warp == T2_W_TMA && lane < p.n_groups) {       // descriptor fetches overlap the barrier / TMEM setup
+    tma_prefetch_desc(&p.tm0[lane]); tma_prefetch_desc(&p.tm1[lane]);
+    if (MODE == T2_DGRAD && p.g[lane].Y.norm.mode == SWR_NORM_BATCH) tma_prefetch_desc(&p.tm2[lane]);
+  }
   t2_setup(sh, tid, warp, T2_NSTAGER / 2, C);
   const uint32_t tmem = sh.tmem_base;
   if (tid == 0) T2_STAMP(0, 127);
@@ -530,7 +539,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
       float acc[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-      float4 pre[8];     // what a pass needs from global memory: raw rows of the destination (dgrad) / pre[0] = bias quad (fwd)
+      float4 pre[4];     // what a pass needs from global memory: the next raw rows of the destination (dgrad) / pre[0] = bias quad (fwd)
       {
         // Only what the drain loop needs is decoded here (the tile is decoded again below): the running sums take 64
         // registers, and everything else that lives across the loop pushes them into local memory.
@@ -591,8 +600,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
       const bool base_al = (MODE == T2_FWD) ? ((G.Y.ld % 4 == 0) && is_al16(G.Y.raw))
                                             : ((D.ld % 4 == 0) && is_al16(D.dz) && is_al16(D.raw));
       // Requests of pass sp, issued ahead of its use: the forward's bias quad (pass 0: before the drain loop, above), the
-      // data gradient's raw rows (pass 0: here, eight float4 beside the 64 running sums would not fit the drain loop's
-      // registers; pass 1: behind the row loop of pass 0, hidden by its statistics tail).
+      // first four raw rows of the data gradient (pass 0: here; pass 1: behind the row loop of pass 0, hidden by its
+      // statistics tail); the row loop keeps four rows in flight.
+      // The row loops below are deliberately NOT unrolled: this code runs once or twice per tile, so every instruction is
+      // an instruction-cache miss the first time round -- straight-line code ran at ~40 cycles per instruction here
+      // (stall_no_inst in profiles/r02y), a rolled loop pays that once.
       bool pre_ok = false;
       auto prefetch = [&](int sp) {
         pre_ok = false;
@@ -605,7 +617,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
           const float* src = D.raw + (int64_t)(T.m0 + row_base) * D.ld + n;
           const int64_t ostep = 4 * (int64_t)D.ld;
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
+          for (int i = 0; i < 4; ++i)
             if (i < rows_here) pre[i] = *reinterpret_cast<const float4*>(src + i * ostep);
           pre_ok = true;
         }
@@ -622,6 +634,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
         named_bar(bar_g, 128);                       // the group is done with the previous contents of ot / red
         t2_acc_to_smem(ot_s, arow, sp, pc, acc);
         named_bar(bar_g, 128);
+        if (tid == 32 * T2_NSTAGER) { T2_STAMP(3, ev); ++ev; }
         const int nv = nvalid - c4;                  // valid components of this lane's column quad (<= 0: none)
         const int n = T.n0 + pc0 + c4;               // first output column of the quad
         float4 s1 = t2_zero4(), s2 = t2_zero4();
@@ -635,16 +648,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
             const float4 r0 = lds128(ot_s + (uint32_t)c4 * 4u);      // row 0 of the tile: always a valid batch row
             if (G.e_act == SWR_ACT_NONE && vec) {   // the common case, branch-free per row
               const float4 y0 = make_float4(r0.x + bias.x, r0.y + bias.y, r0.z + bias.z, r0.w + bias.w);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                if (i < rows_here) {
-                  const float4 a = lds128(my_ot + (uint32_t)(4 * i * T2_OT_LD) * 4u);
-                  const float4 y = make_float4(a.x + bias.x, a.y + bias.y, a.z + bias.z, a.w + bias.w);
-                  *reinterpret_cast<float4*>(dst + i * dstep) = y;
-                  const float4 d = make_float4(y.x - y0.x, y.y - y0.y, y.z - y0.z, y.w - y0.w);
-                  s1.x += d.x; s1.y += d.y; s1.z += d.z; s1.w += d.w;
-                  s2.x = fmaf(d.x, d.x, s2.x); s2.y = fmaf(d.y, d.y, s2.y); s2.z = fmaf(d.z, d.z, s2.z); s2.w = fmaf(d.w, d.w, s2.w);
-                }
+#pragma unroll 1
+              for (int i = 0; i < rows_here; ++i) {
+                const float4 a = lds128(my_ot + (uint32_t)(4 * i * T2_OT_LD) * 4u);
+                const float4 y = make_float4(a.x + bias.x, a.y + bias.y, a.z + bias.z, a.w + bias.w);
+                *reinterpret_cast<float4*>(dst + i * dstep) = y;
+                const float4 d = make_float4(y.x - y0.x, y.y - y0.y, y.z - y0.z, y.w - y0.w);
+                s1.x += d.x; s1.y += d.y; s1.z += d.z; s1.w += d.w;
+                s2.x = fmaf(d.x, d.x, s2.x); s2.y = fmaf(d.y, d.y, s2.y); s2.z = fmaf(d.z, d.z, s2.z); s2.w = fmaf(d.w, d.w, s2.w);
               }
             } else {
               const float4 y0 = make_float4(t2_epi_val(r0.x, bias.x, G.e_act, G.e_scale), t2_epi_val(r0.y, bias.y, G.e_act, G.e_scale),
@@ -669,32 +680,78 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
           if (nv > 0) {
             const int cc0 = pc0 + c4;
             const int64_t o0 = (int64_t)(T.m0 + row_base) * D.ld + n, ostep = 4 * (int64_t)D.ld;
-            if (vec && !atomic_dst) {              // the common case
+            const bool full8 = rows_here == 8 && vec && !accumulate;
+            if (full8 && atomic_dst && plainD) {
+              // partial fan-in of a plain destination (the embedding output at level 0), full tile: transposed row -> one
+              // 16-byte reduction, nothing else
+              float* dp = D.dz + o0;
+#pragma unroll 1
+              for (int i = 0; i < 8; ++i, dp += ostep) t2_red_add_v4(dp, lds128(my_ot + (uint32_t)(4 * i * T2_OT_LD) * 4u));
+            } else if (full8 && !atomic_dst && pre_ok && D.act != SWR_ACT_SIGMOID) {
+              // BatchNorm / ReLU-family destination, full tile: the hot case.  Two trips of four rows without guards; pointer
+              // increments instead of per-row address arithmetic (the general loop below spends most of its ~100
+              // instructions per row on addressing and divergence bookkeeping, and two warps per scheduler cannot hide it)
+              const float4 mu = t2_ld4s(ccs + cc0), sc = t2_ld4s(ccs + T.NT + cc0), bb = t2_ld4s(ccs + 2 * T.NT + cc0), rr4 = t2_ld4s(ccs + 3 * T.NT + cc0);
+              const float slope = t2_slope(D.act);
+              const float* rp = D.raw + o0 + 4 * ostep;       // rows 4..7 (rows 0..3 are in pre[])
+              float* dp = D.dz + o0;
+              uint32_t op = my_ot;
+#pragma unroll 1
+              for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float4 dz = lds128(op);
+                  const float4 raw = pre[j];
+                  if (h == 0) pre[j] = *reinterpret_cast<const float4*>(rp);
+                  const float4 xc = make_float4(raw.x - mu.x, raw.y - mu.y, raw.z - mu.z, raw.w - mu.w);
+                  dz.x *= fmaf(xc.x, sc.x, bb.x) > 0.f ? 1.f : slope; dz.y *= fmaf(xc.y, sc.y, bb.y) > 0.f ? 1.f : slope;
+                  dz.z *= fmaf(xc.z, sc.z, bb.z) > 0.f ? 1.f : slope; dz.w *= fmaf(xc.w, sc.w, bb.w) > 0.f ? 1.f : slope;
+                  s1.x += dz.x; s1.y += dz.y; s1.z += dz.z; s1.w += dz.w;
+                  s2.x = fmaf(dz.x, xc.x * rr4.x, s2.x); s2.y = fmaf(dz.y, xc.y * rr4.y, s2.y);
+                  s2.z = fmaf(dz.z, xc.z * rr4.z, s2.z); s2.w = fmaf(dz.w, xc.w * rr4.w, s2.w);
+                  *reinterpret_cast<float4*>(dp) = dz;
+                  dp += ostep; rp += ostep; op += (uint32_t)(4 * T2_OT_LD) * 4u;
+                }
+              }
+            } else if (vec && !atomic_dst) {       // the general aligned case
               const float4 mu = t2_ld4s(ccs + cc0), sc = t2_ld4s(ccs + T.NT + cc0), bb = t2_ld4s(ccs + 2 * T.NT + cc0), rr4 = t2_ld4s(ccs + 3 * T.NT + cc0);
               const float slope = t2_slope(D.act);
               const bool sigD = D.act == SWR_ACT_SIGMOID;
+              const float* rsrc = D.raw + o0;
+              // four rows per trip, so that the in-flight raw rows keep static register names (a rotation through moves
+              // would wait for the youngest load every iteration)
+#pragma unroll 1
+              for (int i0 = 0; i0 < rows_here; i0 += 4) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                if (i < rows_here) {
-                  float4 dz = lds128(my_ot + (uint32_t)(4 * i * T2_OT_LD) * 4u);
-                  float* dst = D.dz + o0 + i * ostep;
-                  if (!plainD) {
-                    const float4 raw = pre_ok ? pre[i] : *reinterpret_cast<const float4*>(D.raw + o0 + i * ostep);
-                    const float4 xc = make_float4(raw.x - mu.x, raw.y - mu.y, raw.z - mu.z, raw.w - mu.w);
-                    const float4 z = make_float4(fmaf(xc.x, sc.x, bb.x), fmaf(xc.y, sc.y, bb.y), fmaf(xc.z, sc.z, bb.z), fmaf(xc.w, sc.w, bb.w));
-                    if (sigD) {
-                      dz.x *= act_grad(z.x, SWR_ACT_SIGMOID); dz.y *= act_grad(z.y, SWR_ACT_SIGMOID);
-                      dz.z *= act_grad(z.z, SWR_ACT_SIGMOID); dz.w *= act_grad(z.w, SWR_ACT_SIGMOID);
-                    } else {       // d max(z, slope z) / dz
-                      dz.x *= z.x > 0.f ? 1.f : slope; dz.y *= z.y > 0.f ? 1.f : slope;
-                      dz.z *= z.z > 0.f ? 1.f : slope; dz.w *= z.w > 0.f ? 1.f : slope;
+                for (int j = 0; j < 4; ++j) {
+                  const int i = i0 + j;
+                  if (i < rows_here) {
+                    float4 dz = lds128(my_ot + (uint32_t)(4 * i * T2_OT_LD) * 4u);
+                    float* dst = D.dz + o0 + i * ostep;
+                    if (!plainD) {
+                      float4 raw;
+                      if (pre_ok) {       // take row i, ask for row i + 4
+                        raw = pre[j];
+                        if (i + 4 < rows_here) pre[j] = *reinterpret_cast<const float4*>(rsrc + (i + 4) * ostep);
+                      } else {
+                        raw = *reinterpret_cast<const float4*>(rsrc + i * ostep);
+                      }
+                      const float4 xc = make_float4(raw.x - mu.x, raw.y - mu.y, raw.z - mu.z, raw.w - mu.w);
+                      const float4 z = make_float4(fmaf(xc.x, sc.x, bb.x), fmaf(xc.y, sc.y, bb.y), fmaf(xc.z, sc.z, bb.z), fmaf(xc.w, sc.w, bb.w));
+                      if (sigD) {
+                        dz.x *= act_grad(z.x, SWR_ACT_SIGMOID); dz.y *= act_grad(z.y, SWR_ACT_SIGMOID);
+                        dz.z *= act_grad(z.z, SWR_ACT_SIGMOID); dz.w *= act_grad(z.w, SWR_ACT_SIGMOID);
+                      } else {       // d max(z, slope z) / dz
+                        dz.x *= z.x > 0.f ? 1.f : slope; dz.y *= z.y > 0.f ? 1.f : slope;
+                        dz.z *= z.z > 0.f ? 1.f : slope; dz.w *= z.w > 0.f ? 1.f : slope;
+                      }
+                      s1.x += dz.x; s1.y += dz.y; s1.z += dz.z; s1.w += dz.w;
+                      s2.x = fmaf(dz.x, xc.x * rr4.x, s2.x); s2.y = fmaf(dz.y, xc.y * rr4.y, s2.y);
+                      s2.z = fmaf(dz.z, xc.z * rr4.z, s2.z); s2.w = fmaf(dz.w, xc.w * rr4.w, s2.w);
                     }
-                    s1.x += dz.x; s1.y += dz.y; s1.z += dz.z; s1.w += dz.w;
-                    s2.x = fmaf(dz.x, xc.x * rr4.x, s2.x); s2.y = fmaf(dz.y, xc.y * rr4.y, s2.y);
-                    s2.z = fmaf(dz.z, xc.z * rr4.z, s2.z); s2.w = fmaf(dz.w, xc.w * rr4.w, s2.w);
+                    if (accumulate) { const float4 old = *reinterpret_cast<const float4*>(dst); dz.x += old.x; dz.y += old.y; dz.z += old.z; dz.w += old.w; }
+                    *reinterpret_cast<float4*>(dst) = dz;
                   }
-                  if (accumulate) { const float4 old = *reinterpret_cast<const float4*>(dst); dz.x += old.x; dz.y += old.y; dz.z += old.z; dz.w += old.w; }
-                  *reinterpret_cast<float4*>(dst) = dz;
                 }
               }
             } else {
@@ -734,6 +791,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
           }
           prefetch(sp + 1);
         }
+        if (tid == 32 * T2_NSTAGER) { T2_STAMP(3, ev); ++ev; }
         const bool want_stats = (MODE == T2_FWD) ? (G.stats_out != nullptr) : (has_norm && D.dstats != nullptr);
         if (want_stats) {           // uniform over the group
 #pragma unroll
@@ -748,6 +806,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
             *reinterpret_cast<float4*>(red + (1 * 4 + q) * 32 + c4) = s2;
           }
           named_bar(bar_g, 128);
+          if (tid == 32 * T2_NSTAGER) { T2_STAMP(3, ev); ++ev; }
           if (gtid < nvalid && cnt_rows > 0) {      // one thread per column: fp32 sum over the group's warps, widened once
             const float S1 = red[gtid] + red[32 + gtid] + red[64 + gtid] + red[96 + gtid];
             const float S2 = red[128 + gtid] + red[160 + gtid] + red[192 + gtid] + red[224 + gtid];
@@ -809,6 +868,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_wgrad_kernel(const __gri
   int t_begin, t_end;
   t2_range(p, p.n_tiles, 1, t_begin, t_end);
   if (tid == 0) T2_STAMP(0, 126);
+  if (warp == T2_W_TMA && lane < p.n_groups) {
+    tma_prefetch_desc(&p.tm0[lane]); tma_prefetch_desc(&p.tm2[lane]);
+    if (p.g[lane].Y.norm.mode == SWR_NORM_BATCH) tma_prefetch_desc(&p.tm1[lane]);
+  }
   t2_setup(sh, tid, warp, T2_NSTAGER, 1);
   const uint32_t tmem = sh.tmem_base;
   if (tid == 0) T2_STAMP(0, 127);
@@ -864,7 +927,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_wgrad_kernel(const __gri
     }
    }
   } else if (warp < T2_NSTAGER) {
-    reg_dec<T2_REG_STAGER>();
+    /* 96 at launch: nothing to give back */
     const int q = warp & 3, kh = warp >> 2, stid = tid;
     const int nl = 32 * q + lane;                    // output feature inside the tile = TMEM lane
     const uint32_t ta = tmem + T2_A_COL0 + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * kh);
@@ -958,7 +1021,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_wgrad_kernel(const __gri
       }
     }
   } else {
-    reg_inc<T2_REG_EPI>();
+    reg_inc<T2W_REG_EPI>();
     // two independent epilogue groups, see fc_tc2_kernel
     const int e = warp - T2_NSTAGER, q = warp & 3, ch = e >> 2;
     const int arow = 32 * q + lane;
@@ -1267,7 +1330,6 @@ static int t2_grid(K kernel, int n_tiles, int cluster, size_t smem) {
   }
   return max(1, min(min(n_tiles, max_clusters), T2_MAX_CTAS));
 }
-
 // Contiguous tile ranges of (almost) equal cost: the smallest bottleneck cost `cap` for which a greedy walk needs at most
 // `nb` ranges (binary search), then that walk.  cost[t] > 0.
 static void t2_balance(Tc2Params& p, const std::vector<int>& cost, int nb) {
@@ -1605,8 +1667,9 @@ int launch_fc_tc2_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStre
   rc = t2_set_smem(fc_tc2_wgrad_kernel, smem);
   if (rc) return rc;
   p.cluster = 1;
+  const int nb = t2_grid(fc_tc2_wgrad_kernel, tiles, 1, smem);
   T2Debug dbg(p, st);
-  rc = t2_launch(fc_tc2_wgrad_kernel, t2_grid(fc_tc2_wgrad_kernel, tiles, 1, smem), 1, smem, p, st, "fc_tc2_wgrad_kernel");
+  rc = t2_launch(fc_tc2_wgrad_kernel, nb, 1, smem, p, st, "fc_tc2_wgrad_kernel");
   if (rc) return rc;
   dbg.report("wgrad", p, tiles, st);
   return SWR_OK;
