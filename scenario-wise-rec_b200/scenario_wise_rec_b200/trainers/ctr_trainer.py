@@ -221,12 +221,23 @@ class CTRTrainer(object):
             return []
         return torch.cat([c.reshape(-1) for c in chunks]).cpu().tolist()
 
+    def _device_metrics(self) -> bool:
+        """On a CUDA device, with the default metric (sklearn's roc_auc_score, like the reference), AUC and logloss are
+        evaluated on the device (trainers/metrics.py) and only the scalars come back; a user-supplied ``evaluate_fn``
+        keeps receiving Python lists."""
+        return self.device.type == "cuda" and self.evaluate_fn is CTRTrainer.evaluate_fn
+
     def evaluate(self, model, data_loader, mode="val"):
         from sklearn.metrics import log_loss
         targets, predicts = [], []
         for _x, y, y_pred in self._predict_batches(model, data_loader, "validation"):
             targets.append(y)
             predicts.append(y_pred)
+        if targets and self._device_metrics():
+            from .metrics import binary_auc, binary_logloss
+            y = torch.cat([c.reshape(-1) for c in targets]).to(self.device, non_blocking=True)
+            p = torch.cat([c.reshape(-1) for c in predicts])
+            return binary_auc(y, p), binary_logloss(y, p)
         targets, predicts = self._to_list(targets), self._to_list(predicts)
         return self.evaluate_fn(targets, predicts), log_loss(targets, predicts)
 
@@ -239,6 +250,23 @@ class CTRTrainer(object):
             d_chunks.append(x_dict["domain_indicator"])
         if not p_chunks:
             return [None] * domain_num, [None] * domain_num, None, None
+        if self._device_metrics():
+            # per-domain masks, AUC and logloss on the device (ctr_trainer.py:113-152 of the reference builds D pairs of
+            # Python lists); a domain without samples reports None like the reference
+            from .metrics import binary_auc, binary_logloss
+            y = torch.cat([c.reshape(-1) for c in t_chunks]).to(self.device, non_blocking=True)
+            p = torch.cat([c.reshape(-1) for c in p_chunks])
+            dom = torch.cat([c.reshape(-1) for c in d_chunks]).to(self.device)
+            logloss_d, auc_d = [], []
+            for d in range(domain_num):
+                m = dom == d
+                if bool(m.any()):
+                    logloss_d.append(binary_logloss(y[m], p[m]))
+                    auc_d.append(binary_auc(y[m], p[m]))
+                else:
+                    logloss_d.append(None)
+                    auc_d.append(None)
+            return logloss_d, auc_d, binary_logloss(y, p), binary_auc(y, p)
         y = torch.cat([c.reshape(-1) for c in t_chunks]).cpu()
         y_pred = torch.cat([c.reshape(-1) for c in p_chunks]).cpu()
         dom = torch.cat([c.reshape(-1) for c in d_chunks]).cpu()

@@ -60,3 +60,37 @@ def test_evaluate_matches_reference_loop():
     assert ll_d[D] is None and auc_d[D] is None
     assert tr.evaluate_multi_domain_loss(model, [], D) == ([None] * D, [None] * D, None, None)
     assert tr.predict(model, []) == []
+
+
+def test_device_metric_definitions_match_sklearn():
+    """trainers/metrics.py (what CTRTrainer.evaluate uses on a CUDA device) against sklearn on labels / scores with ties,
+    exact 0 and 1 probabilities and a skewed class balance; and sklearn's error behaviour for a single class."""
+    from scenario_wise_rec_b200.trainers.metrics import binary_auc, binary_logloss
+    g = torch.Generator().manual_seed(3)
+    for n in (5, 257, 20000):
+        y = (torch.rand(n, generator=g) < 0.2).float()
+        y[0], y[1] = 1.0, 0.0
+        p = torch.rand(n, generator=g)
+        p[::7] = p[0]                      # ties
+        p[2], p[3] = 0.0, 1.0              # clipped by log_loss
+        assert abs(binary_auc(y, p) - roc_auc_score(y.tolist(), p.tolist())) <= 1e-12
+        ll = log_loss(y.tolist(), p.tolist())
+        assert abs(binary_logloss(y, p) - ll) <= 1e-12 * max(1.0, abs(ll))
+    ones = torch.ones(8)
+    with pytest.raises(ValueError):
+        binary_auc(ones, torch.rand(8))
+    with pytest.raises(ValueError):
+        binary_logloss(ones, torch.rand(8))
+
+
+def test_custom_evaluate_fn_keeps_the_list_path():
+    """A user-supplied metric keeps receiving Python lists (the device metrics replace only the default AUC)."""
+    from scenario_wise_rec_b200.trainers import CTRTrainer
+    assert CTRTrainer.evaluate_fn is CTRTrainer.evaluate_fn
+    t = CTRTrainer.__new__(CTRTrainer)
+    t.device = torch.device("cpu")
+    assert not t._device_metrics()
+    t.device = torch.device("cuda", 0)
+    assert t._device_metrics()
+    t.evaluate_fn = lambda a, b: 0.5
+    assert not t._device_metrics()
