@@ -1273,15 +1273,23 @@ static int t2_set_smem(K kernel, size_t bytes) {
 }
 
 // shared-memory plan: ring B [sb][stage_b] | ring R [sr][stage_r] | coef | ccs | ot | red
-static int t2_plan_smem(Tc2Params& p, size_t stage_b, size_t stage_r, size_t coef_bytes, size_t ccs_bytes, size_t* smem_bytes) {
+// two_groups: the forward / data-gradient kernels, whose two stager groups take alternate k-blocks.  Their raw ring must
+// have an EVEN number of stages, so that a stage always belongs to the same group: with three stages a stage alternates
+// between the groups, each group revisits it only every second pass, and its parity wait is satisfied by the pass in
+// between -- a group running two k-blocks ahead of the other then staged the other group's (older) tile.  That was a
+// latent race (about one forward in forty at B = 16384 with 10+ tiles per CTA, tools/stress_forward.py).
+static int t2_plan_smem(Tc2Params& p, size_t stage_b, size_t stage_r, size_t coef_bytes, size_t ccs_bytes, size_t* smem_bytes,
+                        bool two_groups = true) {
   const size_t fixed = ((coef_bytes + 15) & ~(size_t)15) + ((ccs_bytes + 15) & ~(size_t)15) + T2_OT_BYTES + T2_RED_BYTES;
   // 227 KB opt-in maximum minus static shared memory and alignment slack (SWR_TC_SMEM_KB: experiments with the
   // 196 KB carve-out, which leaves 32 KB of L1, showed no gain)
   static const size_t budget = [] { const char* e = getenv("SWR_TC_SMEM_KB"); return (size_t)(e ? atoi(e) : 224) * 1024 - 1024; }();
-  static const int pref[][2] = {{4, 4}, {4, 3}, {3, 3}, {4, 2}, {3, 2}, {2, 3}, {2, 2}};
+  static const int pref[][2] = {{4, 4}, {4, 3}, {3, 4}, {3, 3}, {4, 2}, {3, 2}, {2, 4}, {2, 3}, {2, 2}};
   int sb = 0, sr = 0;
-  for (auto& c : pref)
+  for (auto& c : pref) {
+    if (two_groups && (c[1] & 1)) continue;
     if (fixed + c[0] * stage_b + c[1] * stage_r <= budget) { sb = c[0]; sr = c[1]; break; }
+  }
   if (!sb) { set_error("fc_tc2: %zu bytes of tables do not fit beside the stage rings", fixed); return SWR_ERR_UNSUPPORTED; }
   p.sb = sb; p.sr = sr; p.stage_b = (int)stage_b; p.stage_r = (int)stage_r;
   size_t off = (size_t)sb * stage_b;
@@ -1662,7 +1670,8 @@ int launch_fc_tc2_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStre
   }
   p.tile_start[n_groups] = tiles; p.n_tiles = tiles; p.flush = flush;
   size_t smem = 0;
-  int rc = t2_plan_smem(p, 2 * (size_t)nt_max * 128, 2 * (size_t)T2_RAW_BYTES + 32 * (size_t)nt_max * 4, 3 * sizeof(float) * (size_t)nt_max, 0, &smem);
+  int rc = t2_plan_smem(p, 2 * (size_t)nt_max * 128, 2 * (size_t)T2_RAW_BYTES + 32 * (size_t)nt_max * 4, 3 * sizeof(float) * (size_t)nt_max, 0, &smem,
+                        false);      // all eight stager warps take every k-block
   if (rc) return rc;
   rc = t2_set_smem(fc_tc2_wgrad_kernel, smem);
   if (rc) return rc;

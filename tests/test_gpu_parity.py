@@ -297,3 +297,32 @@ def test_embedding_layer_standalone():
     emb(x, feats, squeeze_dim=True)
     with pytest.raises(IndexError):
         emb.check_indices()
+
+
+# --------------------------------------------------------------------------------------------
+# run-to-run repeatability of the persistent tcgen05 kernels with many tiles per CTA
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("training", [False, True])
+def test_tensor_core_forward_is_repeatable(training):
+    """HamurSmall at B = 16384 with every layer on the tcgen05 kernels: 10+ tiles per persistent CTA, tiles of mixed cost
+    dealt out through the permutation table.  Eight forwards of the same batch must agree (the only run-to-run freedom is
+    the order of the fp64 statistics atomics, ~1e-7 on the output).  This is the check that exposed a shared-memory tile
+    cache as non-deterministic during round 2 (profiles/r02_fc_tc2_notes.md); a race in the role handshakes shows up
+    here as differences of 1e-2 and more."""
+    prev = N.set_fc_mode(N.FC_TC)
+    try:
+        model_name, cfg, B = BASELINE_CASES["cfg5a_hamursmall_mind_b16384"]
+        x, _y = gpu_util.make_batch(workloads.all_feature_specs(cfg), B, cfg["domain_num"], seed=5, zipf=True)
+        torch.manual_seed(7)
+        model = model_factory.build(model_name, cfg)
+        gpu_util.randomise(model, 11)
+        model.to(DEV).train(training)
+        xg = {k: v.to(DEV) for k, v in x.items()}
+        with torch.no_grad():
+            outs = [model(xg).clone() for _ in range(8)]
+        torch.cuda.synchronize()
+        ref = torch.stack(outs).median(0).values
+        worst = max(float((o - ref).abs().max()) for o in outs)
+        assert worst <= 1e-5, worst
+    finally:
+        N.set_fc_mode(prev)
