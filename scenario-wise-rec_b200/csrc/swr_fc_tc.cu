@@ -96,6 +96,8 @@ static_assert(sizeof(Tc2Params) <= 32764, "kernel parameters are limited to 3276
 // development aid: event `i` of role `role` (0 TMA, 1 MMA, 2 stager warp 0, 3 epilogue warp 8) of CTA 0
 #define T2_STAMP(role, i) do { if (p.dbg && blockIdx.x == 0 && (i) < 128) p.dbg[(role) * 128 + (i)] = clock64(); } while (0)
 
+
+
 struct T2Tile {
   int g;            // fwd / wgrad: group;  dgrad: first group of the destination
   int ge;           // dgrad: one past the last group of the destination
@@ -107,6 +109,7 @@ struct T2Tile {
   int b_begin, b_end;   // wgrad: batch rows of this split
 };
 
+constexpr int T2_TILE_CAP = 32;            // tiles one CTA walks (launches that need more fall back to FFMA)
 
 struct Tc2Shared {
   uint64_t full_b[T2_MAX_STAGES];  // fwd/dgrad: TMA landed the weight tile
@@ -117,7 +120,11 @@ struct Tc2Shared {
   uint64_t empty_a[T2_ASTAGES];    // tcgen05.commit
   uint64_t acc_full[2];            // tcgen05.commit: a partial accumulator is complete
   uint64_t acc_empty[2];           // the epilogue warps have drained it
-  uint32_t tmem_base;
+  alignas(16) uint32_t tmem_base;
+  uint32_t pad_[3];
+  T2Tile tile[T2_TILE_CAP];        // this CTA's tiles, decoded once by an otherwise idle warp: every role reads them here (the
+                                   // search + divisions of the decode are a few hundred instructions per inlined copy, and
+                                   // code that runs once per tile is paid for in instruction-cache misses)
 };
 
 __device__ __forceinline__ uint8_t* t2_align1024(uint8_t* p) {
@@ -295,6 +302,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
   const int C = p.cluster, crank = C > 1 ? (int)cluster_ctarank() : 0;
   t2_range(p, p.n_tiles, C, t_begin, t_end);
   if (tid == 0) T2_STAMP(0, 126);
+  if (warp == T2_W_MMA + 1)
+    for (int i = lane; i < t_end - t_begin; i += 32) sh.tile[i] = t2_decode<MODE>(p, t_begin + i, crank);
   if (warp == T2_W_TMA && lane < p.n_groups) {       // descriptor fetches overlap the barrier / TMEM setup
     tma_prefetch_desc(&p.tm0[lane]); tma_prefetch_desc(&p.tm1[lane]);
     if (MODE == T2_DGRAD && p.g[lane].Y.norm.mode == SWR_NORM_BATCH) tma_prefetch_desc(&p.tm2[lane]);
@@ -313,7 +322,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
     // ring allows; a cursor is a (tile, group, k-block) position in the CTA's k-block sequence.
     struct Cursor { int t, g, ge, kb, nk, m0, n0, NT; T2Ring r; bool done; };
     auto enter = [&](Cursor& c) {
-      const T2Tile T = t2_decode<MODE>(p, c.t, crank);
+      const T2Tile T = sh.tile[c.t - t_begin];
       c.g = T.g; c.ge = T.ge; c.m0 = T.m0; c.n0 = T.n0; c.NT = T.NT; c.kb = 0;
       c.nk = (MODE == T2_FWD) ? T.nkb : p.tile_start[c.g + 1] - p.tile_start[c.g];
     };
@@ -378,7 +387,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
       uint32_t acc_it = 0;
       int ev = 0;
       for (int t = t_begin; t < t_end; ++t) {
-        const T2Tile T = t2_decode<MODE>(p, t, crank);
+        const T2Tile T = sh.tile[t - t_begin];
         const uint32_t b_bytes = (uint32_t)T.NT * 128u;
         const uint32_t idesc = make_idesc_tf32(T2_BM, T.NT, false, false);
         int fpos = 0;
@@ -416,7 +425,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
     if (grp) { rr.next(SR); ra.next(T2_ASTAGES); }
     int kbg = 0, cur_key = -1, ev = 0;     // kbg: k-blocks of the CTA before this tile (its parity picks the group)
     for (int t = t_begin; t < t_end; ++t) {
-      const T2Tile T = t2_decode<MODE>(p, t, crank);
+      const T2Tile T = sh.tile[t - t_begin];
       const int Kc = T.nkb * KBLK;         // padded contraction length of the tile (fwd: K; dgrad: the whole fan-in)
       bool plainA = false, sig = false;
       float slope = 1.f;
@@ -543,7 +552,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
       {
         // Only what the drain loop needs is decoded here (the tile is decoded again below): the running sums take 64
         // registers, and everything else that lives across the loop pushes them into local memory.
-        const T2Tile T0 = t2_decode<MODE>(p, t, crank);
+        const T2Tile T0 = sh.tile[t - t_begin];
         if (MODE == T2_DGRAD) {
           // coefficients of the destination's own norm / activation: [4][NT] mu, s, b, r
           const ActDev& D0 = p.g[T0.g].A;
@@ -575,7 +584,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_kernel(const __grid_cons
       if (tid == 32 * T2_NSTAGER) { T2_STAMP(3, ev); ++ev; }
       int t_again = t;
       asm volatile("" : "+r"(t_again));              // keeps the decode below from being carried through the drain loop
-      const T2Tile T = t2_decode<MODE>(p, t_again, crank);
+      const T2Tile T = sh.tile[t_again - t_begin];
       const int gtid = (tid - 32 * T2_NSTAGER) & 127;
       const int arow = 32 * q + lane;                  // accumulator row this thread drains
       const int rsub = lane >> 3, c4 = (lane & 7) * 4;  // coalesced pass: 8 lanes per row, 4 rows per warp step
@@ -868,6 +877,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_wgrad_kernel(const __gri
   int t_begin, t_end;
   t2_range(p, p.n_tiles, 1, t_begin, t_end);
   if (tid == 0) T2_STAMP(0, 126);
+  if (warp == T2_W_MMA + 1)
+    for (int i = lane; i < t_end - t_begin; i += 32) sh.tile[i] = t2_decode_wgrad(p, t_begin + i);
   if (warp == T2_W_TMA && lane < p.n_groups) {
     tma_prefetch_desc(&p.tm0[lane]); tma_prefetch_desc(&p.tm2[lane]);
     if (p.g[lane].Y.norm.mode == SWR_NORM_BATCH) tma_prefetch_desc(&p.tm1[lane]);
@@ -881,7 +892,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_wgrad_kernel(const __gri
     T2Ring rr; rr.init();
     int ev = 0;
     for (int t = t_begin; t < t_end; ++t) {
-      const T2Tile T = t2_decode_wgrad(p, t);
+      const T2Tile T = sh.tile[t - t_begin];
       const FcGroup& G = p.g[T.g];
       const bool two = G.Y.norm.mode == SWR_NORM_BATCH;
       const uint32_t bytes = (two ? 2u : 1u) * T2_RAW_BYTES + 32u * (uint32_t)T.NT * 4u;
@@ -904,7 +915,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_wgrad_kernel(const __gri
     uint32_t acc_it = 0;
     int ev = 0;
     for (int t = t_begin; t < t_end; ++t) {
-      const T2Tile T = t2_decode_wgrad(p, t);
+      const T2Tile T = sh.tile[t - t_begin];
       const uint32_t b_bytes = (uint32_t)T.NT * 128u;
       const uint32_t idesc = make_idesc_tf32(T2_BM, T.NT, false, true);
       int fpos = 0;
@@ -935,7 +946,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_wgrad_kernel(const __gri
     T2Ring rr, ra; rr.init(); ra.init();
     int cur_g = -1, cur_n0 = -1, ev = 0;
     for (int t = t_begin; t < t_end; ++t) {
-      const T2Tile T = t2_decode_wgrad(p, t);
+      const T2Tile T = sh.tile[t - t_begin];
       if (T.nkb == 0) continue;
       const FcGroup& G = p.g[T.g];
       const int N = G.Y.n, K = G.A.n, NT = T.NT;
@@ -1032,7 +1043,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) fc_tc2_wgrad_kernel(const __gri
     uint32_t acc_it = 0;
     int ev = 0;
     for (int t = t_begin; t < t_end; ++t) {
-      const T2Tile T = t2_decode_wgrad(p, t);
+      const T2Tile T = sh.tile[t - t_begin];
       if (T.nkb == 0) continue;
       const FcGroup& G = p.g[T.g];
       const int N = G.Y.n, K = G.A.n;
@@ -1256,7 +1267,7 @@ static int t2_flush_for(int nt) {
 
 template <class K>
 static int t2_set_smem(K kernel, size_t bytes) {
-  constexpr int kMaxDyn = 227 * 1024 - 1024;
+  constexpr int kMaxDyn = 227 * 1024 - 2048;      // the opt-in maximum covers static (barriers, decoded tiles: ~1.6 KB) + dynamic shared memory
   if (bytes > (size_t)kMaxDyn) { set_error("fc_tc2: %zu bytes of shared memory needed", bytes); return SWR_ERR_UNSUPPORTED; }
   static thread_local const void* done[8] = {nullptr};
   const void* key = reinterpret_cast<const void*>(kernel);
@@ -1338,6 +1349,18 @@ static int t2_grid(K kernel, int n_tiles, int cluster, size_t smem) {
   }
   return max(1, min(min(n_tiles, max_clusters), T2_MAX_CTAS));
 }
+// every CTA must be able to hold its decoded tiles (T2_TILE_CAP): a balanced partition that gives one CTA more (many
+// cheap tiles) is dropped for the equal split; launches whose equal split does not fit are refused (FFMA serves them)
+static int t2_check_ranges(Tc2Params& p, int n_tiles, int n_ctas) {
+  if (p.balanced) {
+    int worst = 0;
+    for (int b = 0; b < n_ctas; ++b) worst = max(worst, (int)p.cta_tile[b + 1] - (int)p.cta_tile[b]);
+    if (worst <= T2_TILE_CAP) return SWR_OK;
+    p.balanced = 0;
+  }
+  return (n_tiles + n_ctas - 1) / n_ctas <= T2_TILE_CAP ? SWR_OK : SWR_ERR_UNSUPPORTED;
+}
+
 // Contiguous tile ranges of (almost) equal cost: the smallest bottleneck cost `cap` for which a greedy walk needs at most
 // `nb` ranges (binary search), then that walk.  cost[t] > 0.
 static void t2_balance(Tc2Params& p, const std::vector<int>& cost, int nb) {
@@ -1534,6 +1557,7 @@ int launch_fc_tc2_fwd(const FcGroup* groups, int n_groups, int64_t B, cudaStream
       cost.insert(cost.end(), p.tile_start[g + 1] - p.tile_start[g], t2_tile_cost(ceil_div(groups[g].A.n, KBLK), p.nt[g]));
     t2_balance(p, cost, nb);
   }
+  if (t2_check_ranges(p, tiles, nb)) return SWR_ERR_UNSUPPORTED;
   T2Debug dbg(p, st);
   rc = t2_launch(fc_tc2_kernel<T2_FWD>, nb, C, smem, p, st, "fc_tc2_kernel<fwd>");
   if (rc) return rc;
@@ -1619,6 +1643,7 @@ int launch_fc_tc2_dgrad(const FcGroup* groups, const int* dst_group_in, int n_ds
       cost.insert(cost.end(), p.dst_tile[d + 1] - p.dst_tile[d], t2_tile_cost(p.tile_start[dst_group[d + 1]] - p.tile_start[dst_group[d]], p.nt[d]));
     t2_balance(p, cost, nb);
   }
+  if (t2_check_ranges(p, tiles, nb)) return SWR_ERR_UNSUPPORTED;
   T2Debug dbg(p, st);
   rc = t2_launch(fc_tc2_kernel<T2_DGRAD>, nb, C, smem, p, st, "fc_tc2_kernel<dgrad>");
   if (rc) return rc;
@@ -1677,6 +1702,7 @@ int launch_fc_tc2_wgrad(const FcGroup* groups, int n_groups, int64_t B, cudaStre
   if (rc) return rc;
   p.cluster = 1;
   const int nb = t2_grid(fc_tc2_wgrad_kernel, tiles, 1, smem);
+  if (t2_check_ranges(p, tiles, nb)) return SWR_ERR_UNSUPPORTED;
   T2Debug dbg(p, st);
   rc = t2_launch(fc_tc2_wgrad_kernel, nb, 1, smem, p, st, "fc_tc2_wgrad_kernel");
   if (rc) return rc;
