@@ -321,10 +321,13 @@ static int run_bmv(const swr_rec_t& h, const swr_rec_t* subs, bool bwd, Ctx& c, 
 
 // ---- side stream --------------------------------------------------------------------------------------------
 // Ops whose results nothing later in the same program reads -- the weight gradients (consumed by the optimizer, after
-// the program) and the running-statistics update of BatchNorm -- are enqueued on a second stream that forks from the
-// caller's stream at the op and joins it again at the end of the program, so the latency-bound narrow layers of the
-// data-gradient chain and their weight gradients overlap.  Under stream capture the fork / join events become graph
-// edges.  SWR_SIDE_STREAM=0 keeps everything on the caller's stream.
+// the program) -- are enqueued on a second stream that forks from the caller's stream at the op and joins it again at
+// the end of the program, so the latency-bound narrow layers of the data-gradient chain and their weight gradients
+// overlap.  Under stream capture the fork / join events become graph edges.
+// SWR_SIDE_STREAM is a mask: bit 0 = weight gradients (default), bit 1 = the BatchNorm running-statistics update.  The
+// latter is OFF: with it the fused step of the STAR / HAMUR-large / PLE goldens lost parity intermittently (8 of 8 runs
+// of tests/test_gpu_trainer.py -k reference_loop had a failure; 0 of 6 with bit 0 alone, 0 of 8 with no side stream;
+// gpurun_out/r03n_flaky.log, r03o_flaky_mask1.log) -- cause not isolated, and the op is 5 us.
 struct SideStream {
   cudaStream_t s = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
@@ -360,7 +363,7 @@ struct SideStream {
 static thread_local SideStream g_side;
 // bit 0: weight gradients, bit 1: BatchNorm running-statistics update
 static int side_mask() {
-  static const int m = [] { const char* e = getenv("SWR_SIDE_STREAM"); return e ? atoi(e) : 3; }();
+  static const int m = [] { const char* e = getenv("SWR_SIDE_STREAM"); return e ? atoi(e) : 1; }();
   return m;
 }
 static bool side_enabled() { return side_mask() != 0; }
